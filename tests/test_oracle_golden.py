@@ -1,0 +1,158 @@
+"""Pin oracle/kdiff_oracle.py against fixtures produced by the real reference (oracle/make_golden.py).
+
+CPU only.  Bit-exact where the reference arithmetic is reproduced op for op (schedules, integer
+schedule indices, position grids, RoPE frequencies, masks); rtol 1e-3 / atol 1e-5 for model outputs
+and sampler trajectories (the oracle uses explicit softmax instead of SDPA's fused CPU kernel).
+"""
+import torch
+
+from conftest import assert_close, bits, load_fixture, load_npz, synth_sd, unhex
+from oracle import kdiff_oracle as O
+
+
+def test_schedules_bit_exact(kat):
+    fns = dict(karras=O.get_sigmas_karras, exponential=O.get_sigmas_exponential,
+               polyexponential=O.get_sigmas_polyexponential, vp=O.get_sigmas_vp)
+    assert len(kat["schedules"]) >= 10
+    for e in kat["schedules"]:
+        assert bits(fns[e["fn"]](*e["args"])) == e["hex"], e
+
+
+def test_survey_karras_hex():
+    # SURVEY.md section 8c known-answer vector, recorded independently of make_golden.py
+    want = "429ffffe 42320d70 41bbcc01 4139b71d 40a9ba6e 400c86a7 3f4cdeb4 3e7bde3d 3d739676 3c23d706 00000000".split()
+    assert bits(O.get_sigmas_karras(10, 1e-2, 80)) == want
+
+
+def test_ancestral_step(kat):
+    for e in kat["ancestral"]:
+        d, u = O.get_ancestral_step(unhex([e["sigma_from"]])[0], unhex([e["sigma_to"]])[0], eta=e["eta"])
+        assert float(d) == e["down"] and float(u) == e["up"], e
+
+
+def test_toy_sampler_kats(kat):
+    sig = O.get_sigmas_karras(5, 1e-2, 80)
+    toy = lambda x, s, **kw: 0.5 * x
+    x = torch.ones(2, 1, 4, 4)
+    for name in ("sample_euler", "sample_heun", "sample_dpmpp_2m"):
+        got = float(getattr(O, name)(toy, x, sig).flatten()[0])
+        assert got == kat["toy"][name], name
+    # SURVEY.md section 8c values
+    assert abs(kat["toy"]["sample_heun"] - 0.02896302566) < 1e-9
+    assert abs(kat["toy"]["sample_dpmpp_2m"] + 0.03126364946) < 1e-9
+
+
+def test_nonlinear_toy_samplers_bit_exact():
+    z = load_npz("toy_samplers.npz")
+    toy2 = lambda x, s, **kw: x / (1 + s[:, None, None, None] ** 2) + 0.1 * torch.tanh(x)
+    for name in ("sample_euler", "sample_heun", "sample_dpmpp_2m"):
+        assert torch.equal(getattr(O, name)(toy2, z["x"], z["sigmas"]), z[name]), name
+    it = iter(z["noise"])
+    assert torch.equal(O.sample_euler_ancestral(toy2, z["x"], z["sigmas"], noise_sampler=lambda a, b: next(it)), z["sample_euler_ancestral"])
+    it = iter(z["noise"])
+    got = O.sample_euler_ancestral(toy2, z["x"], z["sigmas"], eta=0.5, s_noise=0.9, noise_sampler=lambda a, b: next(it))
+    assert torch.equal(got, z["sample_euler_ancestral_eta05"])
+
+
+def _discrete():
+    betas = torch.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000) ** 2
+    ac = torch.cumprod(1 - betas, 0)
+    return O.DiscreteScheduleOracle(((1 - ac) / ac) ** 0.5, True)
+
+
+def test_discrete_schedule(kat):
+    d, ds = kat["discrete"], _discrete()
+    assert bits(ds.get_sigmas(10)) == d["get_sigmas_10"]
+    assert bits(ds.get_sigmas(37)) == d["get_sigmas_37"]
+    full = ds.get_sigmas()
+    assert len(full) == d["get_sigmas_all_len"] == 1001
+    assert bits(full[:5]) == d["get_sigmas_all_head"] and bits(full[-5:]) == d["get_sigmas_all_tail"]
+    t = ds.sigma_to_t(ds.get_sigmas(10)[:-1])
+    assert t.dtype == torch.int64 and t.tolist() == d["roundtrip_t"] == [999, 888, 777, 666, 555, 444, 333, 222, 111, 0]
+    q = unhex(d["query"])
+    assert ds.sigma_to_t(q).tolist() == d["t_quant"]
+    assert bits(ds.sigma_to_t(q, quantize=False)) == d["t_interp"]
+    assert bits(ds.t_to_sigma(torch.tensor([0.0, 0.5, 17.25, 998.9, 999.0]))) == d["t_to_sigma"]
+
+
+def test_scalings(kat):
+    s = kat["scalings"]
+    cs, co, ci = O.karras_scalings(torch.tensor(s["sigma"]), s["sigma_data"])
+    assert bits(cs) == s["c_skip"] and bits(co) == s["c_out"] and bits(ci) == s["c_in"]
+
+
+def test_layer_kats(kat):
+    L = kat["layers"]
+    assert bits(O.rope_freqs(64, 2)) == L["rope_freqs_32_2"]
+    assert bits(O.rope_freqs(64, 8)) == L["rope_freqs_32_8"]
+    assert bits(O.make_axial_pos(4, 4)) == L["axial_pos_4_4"]
+    assert bits(O.make_axial_pos(7, 7)) == L["axial_pos_7_7"]
+    assert bits(O.make_axial_pos(4, 8)) == L["axial_pos_4_8"]
+    assert bits(O.downscale_pos(O.make_axial_pos(8, 8))) == L["downscale_pos_8_8"]
+    m = O.shifted_window_allow(2, 3, 4, 2)
+    assert "".join("1" if b else "0" for b in m.flatten().tolist()) == L["sw_mask_2_3_4_4_2"]
+    a = torch.arange(16.0).view(1, 4, 4, 1)
+    assert O.token_merge(a, torch.eye(4), 2, 2).flatten().tolist() == L["token_merge_4x4"]
+
+
+def test_cfg1_mnist_forward_and_samplers():
+    cfg, shapes, z = load_fixture("cfg1_mnist")
+    sd, mcfg = synth_sd(shapes), cfg["model"]
+    x, cc = z["x"], z["class_cond"]
+    assert_close(O.model_forward(sd, mcfg, x * 0.01, z["sigma"], class_cond=cc), z["inner"], what="inner")
+    assert_close(O.model_forward(sd, mcfg, x * 0.01, z["sigma"], aug_cond=z["aug_cond"], class_cond=cc), z["inner_aug"], what="inner_aug")
+    model = O.make_denoiser(sd, mcfg)
+    assert_close(model(x, z["sigma"], class_cond=cc), z["denoised"], what="denoised")
+    ea = dict(class_cond=cc)
+    assert_close(O.sample_heun(model, x, z["sigmas"], ea), z["heun"], what="heun")
+    assert_close(O.sample_dpmpp_2m(model, x, z["sigmas"], ea), z["dpmpp_2m"], what="dpmpp_2m")
+    assert_close(O.sample_euler(model, x, z["sigmas"], ea), z["euler"], what="euler")
+    it = iter(z["noise"])
+    assert_close(O.sample_euler_ancestral(model, x, z["sigmas"], ea, noise_sampler=lambda a, b: next(it)), z["euler_ancestral"], what="euler_a")
+    assert z["inner"].abs().max() > 1e-3      # not the vacuous all-zero model
+
+
+def test_sw64_forward_and_samplers():
+    cfg, shapes, z = load_fixture("sw64")
+    sd, mcfg = synth_sd(shapes), cfg["model"]
+    assert_close(O.model_forward(sd, mcfg, z["x"] * 0.01, z["sigma"]), z["inner"], what="inner")
+    model = O.make_denoiser(sd, mcfg)
+    assert_close(model(z["x"], z["sigma"]), z["denoised"], what="denoised")
+    assert_close(O.sample_heun(model, z["x"], z["sigmas"]), z["heun"], what="heun")
+    assert_close(O.sample_dpmpp_2m(model, z["x"], z["sigmas"]), z["dpmpp_2m"], what="dpmpp_2m")
+
+
+def test_cfg2_sw256_forward():
+    cfg, shapes, z = load_fixture("cfg2_sw256")
+    sd, mcfg = synth_sd(shapes), cfg["model"]
+    g = torch.Generator().manual_seed(int(z["seed"]))
+    x = torch.randn(1, 3, 256, 256, generator=g) * 160
+    o = O.model_forward(sd, mcfg, x * 0.01, z["sigma"])
+    assert_close(o[..., ::4, ::4], z["inner_sub"], what="inner_sub")
+    assert abs(o.double().mean().item() - float(z["inner_mean"])) < 1e-6
+    assert abs(o.double().pow(2).mean().item() / float(z["inner_sqmean"]) - 1) < 1e-4
+    assert_close(O.make_denoiser(sd, mcfg)(x, z["sigma"])[..., ::4, ::4], z["denoised_sub"], what="denoised_sub")
+
+
+def test_macs_match_reference_counter():
+    import json
+    from conftest import GOLDEN
+    macs = json.loads((GOLDEN / "macs.json").read_text())
+    cfg1 = json.loads((GOLDEN / "cfg1_mnist_shapes.json").read_text())["config"]["model"]
+    cfg2 = json.loads((GOLDEN / "cfg2_sw256_shapes.json").read_text())["config"]["model"]
+    assert O.model_macs(cfg1) == macs["cfg1_mnist"] == 346566656
+    assert O.model_macs(cfg2) == macs["cfg2_sw256"] == 11730419712
+
+
+def test_neighborhood_definition_properties():
+    """natten is absent (parity unpinned): check the restated definition's invariants instead."""
+    allow = O.neighborhood_allow(9, 12, 7)
+    assert allow.shape == (108, 108) and bool((allow.sum(-1) == 49).all())
+    a = allow.view(9, 12, 9, 12)
+    assert bool(a[4, 6, 1:8, 3:10].all()) and not bool(a[4, 6, 0].any())              # interior: centred
+    assert bool(a[0, 0, 0:7, 0:7].all()) and int(a[0, 0].sum()) == 49                 # corner: clamped inward
+    assert bool(a[8, 11, 2:9, 5:12].all())
+    # kernel covering the whole grid == global attention
+    g = torch.Generator().manual_seed(0)
+    q, k, v = (torch.randn(2, 7, 7, 2, 8, generator=g) for _ in range(3))
+    assert_close(O.neighborhood_attention(q, k, v, 7), O.global_attention(q, k, v), what="na==global")
