@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of the k-diffusion sampling hot path on B200.
+
+One "step" = one complete `sample_heun` call (50 Karras steps = 99 denoiser evaluations) over one
+batch of 32 synthetic 256x256x3 latents per GPU on the image_transformer_v2 oxford-flowers
+shifted-window model (BASELINE.json configs[1]).  Weak scaling: every rank samples its own 32.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]             # N>1: launched by torch.distributed.run
+    python bench.py --impl reference ...                            # the reference algorithm's CPU port (oracle/)
+
+Prints ONE JSON line on rank 0 (see the contract in the task statement / DESIGN.md section 6).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+for p in (str(ROOT), str(ROOT / "k-diffusion_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch
+
+METRIC = "images/sec (256x256, Heun 50-step)"
+UNIT = "images/s"
+CFG_FIXTURE = ROOT / "tests" / "golden" / "cfg2_sw256_shapes.json"     # reference config_oxford_flowers_shifted_window.json + defaults
+SAMPLER_STEPS, SIGMA_MIN, SIGMA_MAX, RES, PER_GPU_BATCH = 50, 1e-2, 160.0, 256, 32
+NFE = 2 * SAMPLER_STEPS - 1
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch (default: the BASELINE config)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the roofline and cpu_baseline legs")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
+    return ap.parse_args()
+
+
+def workload_config(n_gpus, batch):
+    return {"workload": f"sample_heun {SAMPLER_STEPS} steps ({NFE} model evaluations), image_transformer_v2 {RES}x{RES} "
+                        "(oxford_flowers shifted-window config), synthetic seeded weights, Karras schedule rho=7 "
+                        f"sigma [{SIGMA_MIN}, {SIGMA_MAX}], batch {batch} per GPU",
+            "sampler": "heun", "sampler_steps": SAMPLER_STEPS, "nfe_per_image": NFE, "resolution": RES,
+            "per_gpu_batch": batch, "global_batch": batch * n_gpus, "parallelism": f"dp{n_gpus} (batch shards, no per-step collective)",
+            "l2": "256 MiB buffer rewritten between timed steps; per-step activation working set also exceeds the 126 MB L2"}
+
+
+def model_config():
+    return json.loads(CFG_FIXTURE.read_text())["config"]
+
+
+def linear_macs_per_image(mcfg):
+    """MACs of every nn.Linear on the token stream per image per model evaluation (reference flops.py:40-41)."""
+    widths, depths, d_ffs = mcfg["widths"], mcfg["depths"], mcfg["d_ffs"]
+    ph, pw = mcfg["patch_size"]
+    t = (mcfg["input_size"][0] // ph) * (mcfg["input_size"][1] // pw)
+    total, n = 0, len(widths)
+    for i, (w, d, f) in enumerate(zip(widths, depths, d_ffs)):
+        layers = d * (1 if i == n - 1 else 2)
+        attn = 0 if mcfg["self_attns"][i]["type"] == "none" else 4 * w * w
+        total += layers * t * (attn + 3 * w * f)
+        if i < n - 1:
+            total += (t // 4) * 4 * w * widths[i + 1] * 2
+        t //= 4
+    return total
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+    def __init__(self, index):
+        self.lines, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "nvidia-smi unavailable"}
+        self.proc.terminate()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ts, line in self.lines:
+            if not (t0 <= ts <= t1 + 0.3):
+                continue
+            f = [v.strip() for v in line.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(self.NAMES, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (the ONLY place bench.py touches oracle/)
+# ------------------------------------------------------------------------------------------------
+def cpu_port_setup():
+    from oracle import kdiff_oracle as O
+    from tests.conftest import synth_sd
+    meta = json.loads(CFG_FIXTURE.read_text())
+    sd = synth_sd(meta["shapes"], 1)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    return O, O.make_denoiser(sd, meta["config"]["model"]), cores
+
+
+def cpu_port_time(O, model, batch, budget_s):
+    """Time the oracle's sample_heun on `batch` images with as many Karras steps as fit the budget; scale to 99 NFE."""
+    g = torch.Generator().manual_seed(123)
+    x = torch.randn(batch, 3, RES, RES, generator=g) * SIGMA_MAX
+    t0 = time.perf_counter()
+    model(x, torch.full([batch], 1.0))
+    t_fwd = time.perf_counter() - t0
+    steps = max(2, min(SAMPLER_STEPS, int((budget_s / max(t_fwd, 1e-3) + 1) // 2)))
+    sigmas = O.get_sigmas_karras(steps, SIGMA_MIN, SIGMA_MAX)
+    t0 = time.perf_counter()
+    O.sample_heun(model, x, sigmas)
+    dt = time.perf_counter() - t0
+    nfe = 2 * steps - 1
+    ips = batch / (dt * NFE / nfe)
+    return ips, f"{batch} image(s) x {nfe} of {NFE} model evaluations (Heun {steps} of {SAMPLER_STEPS} Karras steps) in {dt:.1f} s, scaled by NFE"
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    O, model, cores = cpu_port_setup()
+    total_budget = 170.0
+    per = total_budget / max(1, args.steps + args.warmup)
+    vals, sample = [], ""
+    for i in range(args.warmup + args.steps):
+        ips, sample = cpu_port_time(O, model, 1, per)
+        if i >= args.warmup:
+            vals.append(ips)
+    v = len(vals) / sum(1.0 / a for a in vals)
+    line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * PER_GPU_BATCH / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp32", "data": "synthetic", "impl": "reference", "config": workload_config(args.gpus, args.batch),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "per step: " + sample + "; CPU torch fp32 port of the reference algorithm (oracle/kdiff_oracle.py); "
+                                       "the reference itself is Python and /root/reference does not travel to the GPU box"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            sys.exit(f"--gpus {args.gpus} needs `python -m torch.distributed.run --nproc-per-node {args.gpus} bench.py ...`")
+        args.gpus = world
+    import torch.distributed as dist
+
+    import k_diffusion as K
+    from k_diffusion import _native
+    S = K.sampling
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = K.config.load_config(model_config())
+    inner = K.config.make_model(cfg)
+    if rank == 0:
+        K.synth.synth_init_(inner, seed=1)
+    inner = inner.to(dev).eval().set_precision(args.precision)
+    bcast_bytes = K.parallel.broadcast_weights(inner, src=0)          # the single collective: weights at init
+    model = K.config.make_denoiser_wrapper(cfg)(inner)
+    B = args.batch
+    lo, hi = K.parallel.shard_range(B * world, rank, world)
+    seeds = K.parallel.sample_seeds(123, lo, hi)
+    x = K.parallel.init_noise(seeds, (3, RES, RES), SIGMA_MAX, dev)
+    sigmas = S.get_sigmas_karras(SAMPLER_STEPS, SIGMA_MIN, SIGMA_MAX, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def step_device(_):
+        flush.zero_()
+        return S.sample_heun(model, x, sigmas, disable=True)
+
+    x_host = x.cpu().pin_memory()
+    out_host = torch.empty_like(x_host).pin_memory()
+
+    def step_e2e(_):
+        flush.zero_()
+        xd = x_host.to(dev, non_blocking=True)                        # H2D of this step's inputs (pinned)
+        out = S.sample_heun(model, xd, sigmas, disable=True)          # public API call
+        out_host.copy_(out, non_blocking=True)                        # D2H of this step's result
+        return out
+
+    def timed(fn, k, w):
+        for i in range(w):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = S.total_kernel_launches()
+        t0 = time.time()
+        e0.record()
+        for i in range(k):
+            fn(i)
+        e1.record()
+        barrier()
+        t1 = time.time()
+        return max_over_ranks(e0.elapsed_time(e1)), S.total_kernel_launches() - n0, t0, t1
+
+    clocks = ClockSampler(local) if rank == 0 else None
+    time.sleep(0.3)
+    ms, launches, t0, t1 = timed(step_device, args.steps, args.warmup)
+    clk = clocks.stop(t0, t1) if clocks else None
+    ms_e2e, _, _, _ = timed(step_e2e, args.steps, 1)
+    out = step_device(0)
+    finite = bool(torch.isfinite(out).all())
+    value = world * B * args.steps / (ms / 1000.0)
+    e2e = world * B * args.steps / (ms_e2e / 1000.0)
+
+    roofline = cpu_baseline = breakdown = None
+    if rank == 0 and not args.no_extras:
+        # --- per-kernel-family device times from one eager (non-graph) pass, same batch, 5 Karras steps (9 evaluations)
+        os.environ["KDB200_CUDA_GRAPH"] = "0"
+        sig5 = S.get_sigmas_karras(5, SIGMA_MIN, SIGMA_MAX, device=dev)
+        S.sample_heun(model, x, sig5, disable=True)
+        torch.cuda.synchronize()
+        with _native.profile() as prof:
+            S.sample_heun(model, x, sig5, disable=True)
+        os.environ["KDB200_CUDA_GRAPH"] = "1"
+        total = sum(t for _, t in prof.by_family.values())
+        breakdown = {f: {"launches": c, "ms": round(t, 3), "share": round(t / total, 4)} for f, (c, t) in
+                     sorted(prof.by_family.items(), key=lambda kv: -kv[1][1])}
+        gemm_fams = [f for f in prof.by_family if f.startswith("gemm")]
+        g_launch = sum(prof.by_family[f][0] for f in gemm_fams)
+        g_ms = sum(prof.by_family[f][1] for f in gemm_fams)
+        flops = 2.0 * linear_macs_per_image(cfg["model"]) * B * 9
+        peaks_file = ROOT / "MEASURED_PEAKS.json"
+        if peaks_file.exists():
+            peak, which = json.loads(peaks_file.read_text())["bf16_tflops_sustained"], "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+        else:
+            peak, which = 1400.0, "fallback (B200_PROFILING.md sustained 1.4 PFLOP/s)"
+        ach = flops / (g_ms / 1000.0) / 1e12
+        roofline = {"bound": "tensor", "kernel": "+".join(sorted(gemm_fams)) + " (all token-stream Linear layers)",
+                    "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4), "peak_source": which,
+                    "avg_launch_us": round(1000.0 * g_ms / max(g_launch, 1), 2), "launches": g_launch,
+                    "share_of_step": round(g_ms / total, 4), "traffic": None,
+                    "how": "CUDA events after every launch of one eager sample_heun (5 Karras steps) at the bench batch; "
+                           "algorithmic flops = 2 x Linear MACs (reference flops.py formulas)"}
+        if world == 1:
+            O, cpu_model, cores = cpu_port_setup()
+            v, sample = cpu_port_time(O, cpu_model, 2, args.cpu_seconds)
+            cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": args.precision, "data": "synthetic", "config": workload_config(world, B),
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "kernel_breakdown": breakdown, "weights_broadcast_bytes": bcast_bytes, "output_finite": finite,
+                "native_library": str(_native.LIB_PATH.relative_to(ROOT))}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,32 @@
+// tc_kernels.cuh -- tcgen05 / TMEM / TMA kernels for the bf16 fast path (sm_100a).
+#pragma once
+#include "model_kernels.cuh"
+
+namespace kdb {
+
+// C[M,N] = A[M,K] W[N,K]^T (+ epilogue), bf16 operands staged by TMA, fp32 accumulators in TMEM.
+bool tc_gemm_supported(int64_t M, int N, int K, const GemmEpi& epi);
+int launch_gemm_tc(const bf16* A, const bf16* W, bf16* C, int64_t M, int N, int K, const GemmEpi& epi, cudaStream_t st);
+
+// up_proj with the GEGLU fused into the epilogue; W rows interleaved 8 value / 8 gate (engine.cu).
+bool tc_gemm_geglu_supported(int64_t M, int N2, int K);
+int launch_gemm_tc_geglu(const bf16* A, const bf16* W_il, bf16* out, int64_t M, int N2, int K, cudaStream_t st);
+
+bool tc_attention_supported(int h, int w, int nh, int e, int attn_type, int attn_param);
+int launch_attention_tc(const bf16* qkv, bf16* out, int B, int h, int w, int nh, int e, int attn_type, int attn_param, int shift,
+                        cudaStream_t st);
+
+template <typename T>
+inline int attention_dispatch(const T* qkv, T* out, int B, int h, int w, int nh, int e, int attn_type, int attn_param, int shift,
+                              cudaStream_t st) {
+  return launch_attention_generic<T>(qkv, out, B, h, w, nh, e, attn_type, attn_param, shift, st);
+}
+template <>
+inline int attention_dispatch<bf16>(const bf16* qkv, bf16* out, int B, int h, int w, int nh, int e, int attn_type, int attn_param,
+                                    int shift, cudaStream_t st) {
+  if (tc_attention_supported(h, w, nh, e, attn_type, attn_param))
+    return launch_attention_tc(qkv, out, B, h, w, nh, e, attn_type, attn_param, shift, st);
+  return launch_attention_generic<bf16>(qkv, out, B, h, w, nh, e, attn_type, attn_param, shift, st);
+}
+
+}  // namespace kdb

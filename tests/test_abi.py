@@ -1,0 +1,42 @@
+"""The C-ABI shared library loads without a GPU and exports every symbol include/*.h declares."""
+import ctypes
+import re
+
+from conftest import ROOT
+
+
+def _declared():
+    text = (ROOT / "include" / "kdiffusion_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(kdb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported_and_bound():
+    from k_diffusion import _native
+    names = _declared()
+    assert len(names) >= 25
+    handle = ctypes.CDLL(str(_native.LIB_PATH))
+    for n in names:
+        assert hasattr(handle, n), f"{n} declared in the header but not exported"
+    assert set(names) == set(_native.SIGNATURES), set(names) ^ set(_native.SIGNATURES)
+    assert _native.lib().kdb_abi_version() == _native.ABI_VERSION
+
+
+def test_error_reporting_without_gpu():
+    from k_diffusion import _native
+    L = _native.lib()
+    rc = L.kdb_solver_lincomb(None, None, 0, None, 0, None)
+    assert rc == -1 and b"n_in" in L.kdb_last_error()
+    cfg = _native.KdbModelConfig()
+    h = ctypes.c_void_p()
+    assert L.kdb_model_create(ctypes.byref(cfg), ctypes.byref(h)) == -1      # n_levels = 0
+    assert _native.launch_count() == 0 or _native.launch_count() > 0        # callable
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from k_diffusion import _native
+    monkeypatch.setattr(_native, "_lib", None)
+    monkeypatch.setattr(_native, "LIB_PATH", tmp_path / "nope.so")
+    import pytest
+    with pytest.raises(_native.NativeLibraryError):
+        _native.lib()

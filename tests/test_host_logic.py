@@ -1,0 +1,169 @@
+"""Host-side logic of the product package, CPU only: schedules (bit-exact), DiscreteSchedule
+(bit-exact integer indices), step plans, config/state-dict compatibility, sharding helpers."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+import k_diffusion as K
+from conftest import GOLDEN, assert_close, bits, load_npz, unhex
+from oracle import kdiff_oracle as O
+
+S = K.sampling
+
+
+def test_schedules_bit_exact(kat):
+    fns = dict(karras=S.get_sigmas_karras, exponential=S.get_sigmas_exponential, polyexponential=S.get_sigmas_polyexponential, vp=S.get_sigmas_vp)
+    for e in kat["schedules"]:
+        assert bits(fns[e["fn"]](*e["args"])) == e["hex"], e
+
+
+def test_discrete_schedule_bit_exact(kat):
+    d = kat["discrete"]
+    betas = torch.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000) ** 2
+    ac = torch.cumprod(1 - betas, 0)
+    ds = K.external.DiscreteSchedule(((1 - ac) / ac) ** 0.5, True)
+    assert float(ds.sigma_min) == d["sigma_min"] and float(ds.sigma_max) == d["sigma_max"]
+    assert bits(ds.get_sigmas(10)) == d["get_sigmas_10"] and bits(ds.get_sigmas(37)) == d["get_sigmas_37"]
+    assert len(ds.get_sigmas()) == 1001 and bits(ds.get_sigmas()[:5]) == d["get_sigmas_all_head"]
+    t = ds.sigma_to_t(ds.get_sigmas(10)[:-1])
+    assert t.dtype == torch.int64 and t.tolist() == d["roundtrip_t"]
+    q = unhex(d["query"])
+    assert ds.sigma_to_t(q).tolist() == d["t_quant"]
+    assert bits(ds.sigma_to_t(q, quantize=False)) == d["t_interp"]
+    assert bits(ds.t_to_sigma(torch.tensor([0.0, 0.5, 17.25, 998.9, 999.0]))) == d["t_to_sigma"]
+    assert set(ds.state_dict()) == {"sigmas", "log_sigmas"}
+
+
+def test_ancestral_step_and_scalings(kat):
+    for e in kat["ancestral"]:
+        d, u = S.get_ancestral_step(unhex([e["sigma_from"]])[0], unhex([e["sigma_to"]])[0], eta=e["eta"])
+        assert float(d) == e["down"] and float(u) == e["up"]
+    s = kat["scalings"]
+    cs, co, ci = K.Denoiser(None, sigma_data=s["sigma_data"]).get_scalings(torch.tensor(s["sigma"]))
+    for got, want in ((cs, s["c_skip"]), (co, s["c_out"]), (ci, s["c_in"])):
+        assert_close(got, unhex(want), rtol=2e-7, atol=0)
+
+
+def _exec_plan(kind, plan, model, x, noise=None):
+    """numpy executor of a step plan: what the fused kernels compute, on the CPU, for plan verification only."""
+    x = x.clone()
+    B = x.shape[0]
+    old = None
+    for st in plan:
+        if kind in ("euler", "heun"):
+            den = model(x, torch.full([B], st["sigma_hat"]))
+            if kind == "euler" or st["last"]:
+                x = x + (x - den) * np.float32(st["r"])
+            else:
+                x2 = x + (x - den) * np.float32(st["r"])
+                den2 = model(x2, torch.full([B], st["sigma_next"]))
+                x = x + ((x - den) * np.float32(st["a1"]) + (x2 - den2) * np.float32(st["a2"]))
+        elif kind == "euler_a":
+            den = model(x, torch.full([B], st["sigma"]))
+            x = x + (x - den) * np.float32(st["r"])
+            if st["noise"]:
+                x = x + noise[st["i"]] * np.float32(st["cn"])
+        else:
+            den = model(x, torch.full([B], st["sigma"]))
+            x = np.float32(st["a"]) * x - np.float32(st["b"]) * (np.float32(st["k1"]) * den + (np.float32(st["k0"]) * old if old is not None else 0))
+            old = den
+    return x
+
+
+def test_step_plans_reproduce_reference_trajectories():
+    z = load_npz("toy_samplers.npz")
+    toy2 = lambda x, s, **kw: x / (1 + s[:, None, None, None] ** 2) + 0.1 * torch.tanh(x)
+    sig = S.host_sigmas(z["sigmas"])
+    cases = [("euler", S.plan_euler(sig), "sample_euler"), ("heun", S.plan_heun(sig), "sample_heun"),
+             ("dpmpp", S.plan_dpmpp_2m(sig), "sample_dpmpp_2m")]
+    for kind, plan, key in cases:
+        assert_close(_exec_plan(kind, plan, toy2, z["x"]), z[key], rtol=1e-4, atol=1e-5, what=key)
+    assert_close(_exec_plan("euler_a", S.plan_euler_ancestral(sig), toy2, z["x"], z["noise"]), z["sample_euler_ancestral"], rtol=1e-4, atol=1e-5)
+    assert_close(_exec_plan("euler_a", S.plan_euler_ancestral(sig, eta=0.5, s_noise=0.9), toy2, z["x"], z["noise"]),
+                 z["sample_euler_ancestral_eta05"], rtol=1e-4, atol=1e-5)
+
+
+def test_plan_details():
+    sig = S.host_sigmas(S.get_sigmas_karras(50, 1e-2, 160))
+    heun = S.plan_heun(sig)
+    assert sum(len(st["evals"]) for st in heun) == 99                       # NFE of Heun-50
+    assert heun[-1]["last"] and heun[-1]["r"] == -1.0                       # final Euler step lands on denoised
+    assert sum(len(st["evals"]) for st in S.plan_dpmpp_2m(S.host_sigmas(S.get_sigmas_karras(25, 1e-2, 160)))) == 25
+    d = S.plan_dpmpp_2m(sig)
+    assert d[0]["k0"] == 0 and d[-1]["a"] == 0 and d[-1]["b"] == -1 and d[-1]["k0"] == 0
+    ch = S.plan_heun(sig, s_churn=40, s_tmin=0.05, s_tmax=50)
+    on = [st for st in ch if st["gamma"] > 0]
+    assert on and all(0.05 <= sig[st["i"]] <= 50 for st in on) and all(abs(st["gamma"] - (2 ** 0.5 - 1)) < 1e-12 for st in on)
+    ea = S.plan_euler_ancestral(sig)
+    assert not ea[-1]["noise"] and ea[-1]["r"] == -1.0 and all(st["noise"] for st in ea[:-1])
+    with pytest.raises(ValueError):
+        S.host_sigmas(torch.zeros(1))
+
+
+@pytest.mark.parametrize("stem", ["cfg1_mnist", "sw64", "cfg2_sw256"])
+def test_config_and_state_dict_match_reference(stem):
+    meta = json.loads((GOLDEN / f"{stem}_shapes.json").read_text())
+    raw = {"model": {k: v for k, v in meta["config"]["model"].items()}, "dataset": meta["config"]["dataset"]}
+    cfg = K.config.load_config(raw)
+    assert cfg["model"] == meta["config"]["model"]
+    model = K.config.make_model(cfg)
+    assert {k: list(v.shape) for k, v in model.state_dict().items()} == meta["shapes"]
+    den = K.config.make_denoiser_wrapper(cfg)(model)
+    assert den.sigma_data == cfg["model"]["sigma_data"] and den.inner_model is model
+
+
+def test_config_defaults_from_minimal_json():
+    cfg = K.config.load_config({"model": {"type": "image_transformer_v2", "input_channels": 3, "input_size": [64, 64], "patch_size": [4, 4],
+                                          "depths": [2, 2], "widths": [128, 256]}})
+    ref = json.loads((GOLDEN / "cfg3_na256_config.json").read_text())["config"]
+    assert cfg["model"]["self_attns"] == [{"type": "neighborhood", "d_head": 64, "kernel_size": 7}, {"type": "global", "d_head": 64}]
+    assert cfg["model"]["d_ffs"] == [384, 768] and cfg["model"]["mapping_d_ff"] == 768 and cfg["model"]["dropout_rate"] == [0.0, 0.0]
+    assert set(cfg) == set(ref)
+    with pytest.raises(ValueError):
+        K.config.load_config({"model": {"type": "image_v1"}})
+
+
+def test_fresh_model_init_matches_reference_distribution():
+    torch.manual_seed(0)
+    cfg = K.config.load_config(json.loads((GOLDEN / "cfg1_mnist_shapes.json").read_text())["config"])
+    sd = K.config.make_model(cfg).state_dict()
+    for k, v in sd.items():
+        if k.endswith(("out_proj.weight", "down_proj.weight", "norm.linear.weight", "patch_out.proj.weight")):
+            assert not v.any(), k                                           # zero-initialised in the reference
+    assert torch.all(sd["mid_level.0.self_attn.scale"] == 10) and float(sd["out_norm.scale"].mean()) == 1
+    w = sd["mid_level.0.self_attn.qkv_proj.weight"]
+    assert abs(float(w.std()) - (1 / 256 ** 0.5) / 3 ** 0.5) < 2e-3 and float(w.abs().max()) <= 1 / 16
+    assert bits(sd["mid_level.3.self_attn.pos_emb.freqs"]) == bits(O.rope_freqs(64, 4))
+
+
+def test_cpu_tensors_are_rejected_not_emulated():
+    cfg = K.config.load_config(json.loads((GOLDEN / "cfg1_mnist_shapes.json").read_text())["config"])
+    model = K.Denoiser(K.config.make_model(cfg), sigma_data=0.6162)
+    x = torch.zeros(1, 1, 28, 28)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model(x, torch.ones(1), class_cond=torch.zeros(1, dtype=torch.long))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        S.sample_heun(lambda x, s: x, x, S.get_sigmas_karras(3, 0.1, 10))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        S.to_d(x, torch.ones(()), x)
+
+
+def test_synth_weights_are_order_independent():
+    a = K.synth.synth_tensor("mid_level.0.ff.up_proj.weight", (8, 4), seed=1)
+    b = K.synth.synth_tensor("mid_level.0.ff.up_proj.weight", (8, 4), seed=1)
+    c = K.synth.synth_tensor("mid_level.0.ff.up_proj.weight", (8, 4), seed=2)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    assert float(K.synth.synth_tensor("x.out_proj.weight", (64, 64), 0).std()) < 0.03
+
+
+def test_shard_helpers():
+    P = K.parallel
+    for n, w in [(256, 8), (10, 4), (3, 8), (128, 1)]:
+        spans = [P.shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+    full = P.sample_seeds(7, 0, 16)
+    assert len(set(full)) == 16 and all(0 <= s < 2 ** 63 for s in full)
+    assert P.sample_seeds(7, 4, 9) == full[4:9] and P.sample_seeds(8, 0, 16) != full
