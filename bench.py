@@ -123,7 +123,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 def cpu_port_setup():
     from oracle import kdiff_oracle as O
-    from tests.conftest import synth_sd
+    from oracle.fixtures import synth_sd
     meta = json.loads(CFG_FIXTURE.read_text())
     sd = synth_sd(meta["shapes"], 1)
     cores = os.cpu_count() or 1

@@ -1,26 +1,344 @@
-// tc_kernels.cu -- placeholder until the tcgen05 kernels land (next commit): everything reports
-// "unsupported" so the engine takes the SIMT path.
+// tc_kernels.cu -- bf16 tensor-core kernels for sm_100a: TMA (SWIZZLE_128B tiles) -> shared memory ->
+// tcgen05.mma (fp32 accumulators in TMEM) -> tcgen05.ld -> fused epilogue.
+//
+// GEMM:  C[M,N] = A[M,K] W[N,K]^T for every nn.Linear on the token stream (reference
+// image_transformer_v2.py:126-139), epilogues: plain store, +residual (out_proj/down_proj, :396,:493),
+// GEGLU (:89-95, rows of W interleaved 8 value / 8 gate), TokenSplit scatter + lerp (:618-621).
+//
+// Warp roles in a 192-thread CTA: warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator +
+// MMA issuer (one elected lane), warps 2-5 = epilogue (warp w owns TMEM lanes 32*(w%4)..+31).
+// One 128 x BN output tile per CTA; 2-3 CTAs are co-resident per SM so one tile's epilogue overlaps
+// the next tile's loads and MMAs.
+#include "tc_common.cuh"
 #include "tc_kernels.cuh"
 
 namespace kdb {
-bool tc_gemm_supported(int64_t, int, int, const GemmEpi&) { return false; }
-int launch_gemm_tc(const bf16*, const bf16*, bf16*, int64_t, int, int, const GemmEpi&, cudaStream_t) {
-  set_error("tcgen05 GEMM not built");
-  return KDB_ERR_UNSUPPORTED;
+
+// ------------------------------------------------------------------------------------------------
+// tensor maps (driver entry point fetched through the runtime: no link-time libcuda dependency)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
 }
-bool tc_gemm_geglu_supported(int64_t, int, int) { return false; }
-int launch_gemm_tc_geglu(const bf16*, const bf16*, bf16*, int64_t, int, int, cudaStream_t) {
-  set_error("tcgen05 GEMM not built");
-  return KDB_ERR_UNSUPPORTED;
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+  EncodeTiledFn fn = encode_fn();
+  KDB_REQUIRE(fn != nullptr, KDB_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available from this driver");
+  cuuint64_t gd[5];
+  cuuint64_t gs[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) gs[i - 1] = strides_bytes[i - 1];
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  KDB_REQUIRE(r == CUDA_SUCCESS, KDB_ERR_BAD_ARG, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dim0 %llu, box0 %u)", (int)r,
+              rank, (unsigned long long)dims[0], box[0]);
+  return 0;
 }
-bool tc_attention_supported(int, int, int, int, int, int) { return false; }
-int launch_attention_tc(const bf16*, bf16*, int, int, int, int, int, int, int, int, cudaStream_t) {
-  set_error("tcgen05 attention not built");
-  return KDB_ERR_UNSUPPORTED;
+
+// ------------------------------------------------------------------------------------------------
+// GEMM
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int BM = 128, BK = 64;
+constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KiB
+constexpr int MAX_STAGES = 4;
+
+enum TcEpi { TCE_STORE = 0, TCE_RESID = 1, TCE_GEGLU = 2, TCE_SPLIT = 3 };
+
+struct TcParams {
+  bf16* out;
+  const bf16* resid;     // RESID: [M, N];  SPLIT: skip [B, 2hc, 2wc, Cf]
+  const float* fac;
+  int64_t M;
+  int N, K, stages;
+  int hc, wc, Cf;
+};
+
+// fast erf-GELU: erf via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7, far below bf16 resolution)
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = 1.f - poly * t * __expf(-z * z);
+  const float erf = copysignf(erf_abs, x);
+  return 0.5f * x * (1.f + erf);
 }
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUtensorMap tmb,
+                                                      const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr int B_STAGE_BYTES = BN * BK * 2;
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  constexpr uint32_t IDESC = tc::idesc_bf16(BM, BN);
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)p.stages * STAGE_BYTES);
+  uint64_t* empty = full + MAX_STAGES;
+  uint64_t* tmem_full = empty + MAX_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t m0 = (int64_t)blockIdx.y * BM;
+  const int n0 = blockIdx.x * BN;
+  const int nkb = p.K / BK;
+
+  if (threadIdx.x == 0) {
+    tc::tma_prefetch_desc(&tma);
+    tc::tma_prefetch_desc(&tmb);
+    for (int s = 0; s < p.stages; ++s) {
+      tc::mbar_init(&full[s], 1);
+      tc::mbar_init(&empty[s], 1);
+    }
+    tc::mbar_init(tmem_full, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, BN);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (tc::elect_one()) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % p.stages;
+        const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
+        tc::mbar_wait(&empty[s], ph ^ 1u);
+        tc::mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+        uint8_t* a = base + (size_t)s * STAGE_BYTES;
+        tc::tma_load_2d(a, &tma, &full[s], kb * BK, (int)m0);
+        tc::tma_load_2d(a + A_STAGE_BYTES, &tmb, &full[s], kb * BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (tc::elect_one()) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % p.stages;
+        const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
+        tc::mbar_wait(&full[s], ph);
+        tc::tc_fence_after();
+        const uint32_t a_addr = tc::smem_u32(base + (size_t)s * STAGE_BYTES);
+        const uint64_t adesc = tc::smem_desc_k_sw128(a_addr);
+        const uint64_t bdesc = tc::smem_desc_k_sw128(a_addr + A_STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)   // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
+          tc::umma_bf16(tmem, adesc + 2ull * k, bdesc + 2ull * k, IDESC, (uint32_t)((kb | k) != 0));
+        tc::umma_commit(&empty[s]);
+      }
+      tc::umma_commit(tmem_full);
+    }
+  } else {
+    // ---------------- epilogue: TMEM -> registers -> global
+    tc::mbar_wait(tmem_full, 0);
+    tc::tc_fence_after();
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int64_t m = m0 + row;
+    const bool live = m < p.M;
+    float facv = 0.f;
+    if constexpr (EPI == TCE_SPLIT) facv = __ldg(p.fac);
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      float v[32];
+      tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      if (!live) continue;
+      const int n = n0 + c * 32;
+      if constexpr (EPI == TCE_STORE || EPI == TCE_RESID) {
+        uint4* dst = reinterpret_cast<uint4*>(p.out + m * p.N + n);
+        if constexpr (EPI == TCE_RESID) {
+          const uint4* rs = reinterpret_cast<const uint4*>(p.resid + m * p.N + n);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 r = rs[j];
+            const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              float lo, hi;
+              tc::unpack_bf16x2(rw[t], lo, hi);
+              v[j * 8 + t * 2] += lo;
+              v[j * 8 + t * 2 + 1] += hi;
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          dst[j] = make_uint4(tc::pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]), tc::pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]),
+                              tc::pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]), tc::pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]));
+      } else if constexpr (EPI == TCE_GEGLU) {
+        // columns [16g, 16g+8) = value rows, [16g+8, 16g+16) = the matching gate rows; output width N/2
+        uint4* dst = reinterpret_cast<uint4*>(p.out + m * (p.N / 2) + n / 2);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float gate = __bfloat162float(__float2bfloat16_rn(gelu_erf_fast(__bfloat162float(__float2bfloat16_rn(v[g * 16 + 8 + j])))));
+            o[j] = __bfloat162float(__float2bfloat16_rn(v[g * 16 + j])) * gate;
+          }
+          dst[g] = make_uint4(tc::pack_bf16x2(o[0], o[1]), tc::pack_bf16x2(o[2], o[3]), tc::pack_bf16x2(o[4], o[5]),
+                              tc::pack_bf16x2(o[6], o[7]));
+        }
+      } else {
+        // TokenSplit: row m = (b, hy, wx) on the coarse grid; 32 columns inside one (nh, nw) quadrant (Cf % 32 == 0)
+        const int64_t b = m / ((int64_t)p.hc * p.wc);
+        const int r = (int)(m - b * p.hc * p.wc);
+        const int hy = r / p.wc, wx = r - hy * p.wc;
+        const int qd = n / p.Cf, e = n - qd * p.Cf;
+        const int64_t off = ((b * (2 * p.hc) + (2 * hy + (qd >> 1))) * (2 * p.wc) + (2 * wx + (qd & 1))) * p.Cf + e;
+        const uint4* sk = reinterpret_cast<const uint4*>(p.resid + off);
+        uint4* dst = reinterpret_cast<uint4*>(p.out + off);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 r4 = sk[j];
+          const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+          uint32_t ow[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            float lo, hi;
+            tc::unpack_bf16x2(rw[t], lo, hi);
+            const float e0 = __bfloat162float(__float2bfloat16_rn(v[j * 8 + t * 2])), e1 = __bfloat162float(__float2bfloat16_rn(v[j * 8 + t * 2 + 1]));
+            const float d0 = e0 - lo, d1 = e1 - hi;
+            const float o0 = (facv < 0.5f) ? fmaf(facv, d0, lo) : e0 - d0 * (1.f - facv);
+            const float o1 = (facv < 0.5f) ? fmaf(facv, d1, hi) : e1 - d1 * (1.f - facv);
+            ow[t] = tc::pack_bf16x2(o0, o1);
+          }
+          dst[j] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem, BN);
+  }
+}
+
+template <int BN, int EPI>
+int launch_tc(const bf16* A, const bf16* W, const TcParams& p, int64_t n_rows_w, cudaStream_t st) {
+  CUtensorMap ta, tb;
+  {
+    const uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.M};
+    const uint64_t strides[1] = {(uint64_t)p.K * 2};
+    const uint32_t box[2] = {BK, BM};
+    int rc = make_tmap_bf16(&ta, A, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)n_rows_w};
+    const uint64_t strides[1] = {(uint64_t)p.K * 2};
+    const uint32_t box[2] = {BK, BN};
+    int rc = make_tmap_bf16(&tb, W, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  const size_t smem = (size_t)p.stages * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    KDB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)(p.N / BN), (unsigned)ceil_div(p.M, BM));
+  gemm_tc_kernel<BN, EPI><<<grid, 192, smem, st>>>(ta, tb, p);
+  KDB_LAUNCH_CHECK(F_GEMM_TC, st);
+  return 0;
+}
+
+template <int EPI>
+int dispatch_bn(const bf16* A, const bf16* W, const TcParams& p, cudaStream_t st) {
+  if (p.N % 128 == 0) return launch_tc<128, EPI>(A, W, p, p.N, st);
+  return launch_tc<64, EPI>(A, W, p, p.N, st);
+}
+
+bool shape_ok(int64_t M, int N, int K) {
+  return M > 0 && M < (65535LL * BM) && N >= 64 && N % 64 == 0 && K >= 64 && K % 64 == 0;
+}
+
+int pick_stages(int K) {
+  const int nkb = K / BK;
+  return nkb < 3 ? nkb : 3;
+}
+
+}  // namespace
+
+static bool g_tc_disabled = [] {
+  const char* e = getenv("KDB200_DISABLE_TC");
+  return e != nullptr && e[0] == '1';
+}();
+
+bool tc_gemm_supported(int64_t M, int N, int K, const GemmEpi& epi) {
+  if (g_tc_disabled || !shape_ok(M, N, K)) return false;
+  if (epi.mode == EPI_SPLIT_LERP) return epi.C % 32 == 0 && N == 4 * epi.C;
+  return epi.mode == EPI_STORE || epi.mode == EPI_RESID;
+}
+
+int launch_gemm_tc(const bf16* A, const bf16* W, bf16* C, int64_t M, int N, int K, const GemmEpi& epi, cudaStream_t st) {
+  KDB_REQUIRE(shape_ok(M, N, K), KDB_ERR_BAD_SHAPE, "gemm_tc: unsupported shape M=%lld N=%d K=%d", (long long)M, N, K);
+  KDB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0,
+              KDB_ERR_BAD_ARG, "gemm_tc: operands must be 16-byte aligned");
+  TcParams p{};
+  p.out = C;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.stages = pick_stages(K);
+  switch (epi.mode) {
+    case EPI_STORE:
+      return dispatch_bn<TCE_STORE>(A, W, p, st);
+    case EPI_RESID:
+      p.resid = static_cast<const bf16*>(epi.resid);
+      return dispatch_bn<TCE_RESID>(A, W, p, st);
+    case EPI_SPLIT_LERP:
+      p.resid = static_cast<const bf16*>(epi.resid);
+      p.fac = epi.fac;
+      p.hc = epi.hc;
+      p.wc = epi.wc;
+      p.Cf = epi.C;
+      return dispatch_bn<TCE_SPLIT>(A, W, p, st);
+    default:
+      KDB_REQUIRE(false, KDB_ERR_BAD_ARG, "gemm_tc: bad epilogue");
+  }
+}
+
+bool tc_gemm_geglu_supported(int64_t M, int N2, int K) { return !g_tc_disabled && shape_ok(M, N2, K); }
+
+int launch_gemm_tc_geglu(const bf16* A, const bf16* W_il, bf16* out, int64_t M, int N2, int K, cudaStream_t st) {
+  KDB_REQUIRE(shape_ok(M, N2, K), KDB_ERR_BAD_SHAPE, "gemm_tc_geglu: unsupported shape");
+  TcParams p{};
+  p.out = out;
+  p.M = M;
+  p.N = N2;
+  p.K = K;
+  p.stages = pick_stages(K);
+  return dispatch_bn<TCE_GEGLU>(A, W_il, p, st);
+}
+
 }  // namespace kdb
 
-extern "C" int kdb_gemm_bf16(const void*, const void*, void*, int, int, int, void*) {
-  kdb::set_error("tcgen05 GEMM not built");
-  return KDB_ERR_UNSUPPORTED;
+extern "C" int kdb_gemm_bf16(const void* a, const void* w, void* c, int M, int N, int K, void* stream) {
+  using namespace kdb;
+  KDB_REQUIRE(a && w && c, KDB_ERR_BAD_ARG, "gemm_bf16: NULL operand");
+  GemmEpi e;
+  KDB_REQUIRE(shape_ok(M, N, K), KDB_ERR_UNSUPPORTED, "gemm_bf16: needs N %% 64 == 0 and K %% 64 == 0 (got M=%d N=%d K=%d)", M, N, K);
+  return launch_gemm_tc(static_cast<const bf16*>(a), static_cast<const bf16*>(w), static_cast<bf16*>(c), M, N, K, e, (cudaStream_t)stream);
 }

@@ -335,3 +335,29 @@ class Engine:
 
     def tap_count(self):
         return int(lib().kdb_model_tap_count(self._h))
+
+
+# ---------------------------------------------------------------------------------------------
+# stand-alone kernels (unit tests / profiling)
+# ---------------------------------------------------------------------------------------------
+
+def gemm_bf16(a, w):
+    """a [M,K] bf16, w [N,K] bf16 -> [M,N] bf16 on the tcgen05 kernel (N % 64 == 0, K % 64 == 0)."""
+    require_cuda(a, w)
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.is_contiguous() and w.is_contiguous()
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
+    check(lib().kdb_gemm_bf16(ptr(a), ptr(w), ptr(out), M, N, K, stream()))
+    return out
+
+
+def attention(qkv, h, w, n_heads, d_head, attn_type, attn_param=0, shift=0, fast=False):
+    """qkv [B, h*w, 3*n_heads*d_head] (fp32 or bf16, q/k already normalised + rotated) -> [B, h*w, n_heads*d_head]."""
+    require_cuda(qkv)
+    prec = PREC_BF16 if qkv.dtype == torch.bfloat16 else PREC_FP32
+    B = qkv.shape[0]
+    out = torch.empty(B, h * w, n_heads * d_head, dtype=qkv.dtype, device=qkv.device)
+    code = _ATTN_CODE[attn_type] if isinstance(attn_type, str) else attn_type
+    check(lib().kdb_attention(prec, 1 if fast else 0, ptr(qkv.contiguous()), ptr(out), B, h, w, n_heads, d_head, code, attn_param, shift, stream()))
+    return out

@@ -1,0 +1,81 @@
+"""Tensor-core (tcgen05/TMEM/TMA) kernels against a plain PyTorch fp32 reference of the same op."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 128), (128, 64, 64), (256, 384, 128), (8192, 768, 128), (1000, 256, 512),
+                                   (2048, 512, 1536), (196, 768, 256), (4096, 1024, 2048), (32768, 128, 384)])
+def test_gemm_bf16_tcgen05(M, N, K):
+    from k_diffusion import _native as N_
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    a = torch.randn(M, K, device=DEV, generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, device=DEV, generator=g) / K ** 0.5).to(torch.bfloat16)
+    got = N_.gemm_bf16(a, w).float()
+    want = a.float() @ w.float().T
+    err = (got - want).abs()
+    tol = 1e-2 * want.abs() + 2e-2           # one bf16 ulp of the output (2^-8 relative) + accumulation-order slack
+    assert bool((err <= tol).all()), f"max err {float(err.max()):.4f} at {int(err.argmax())}, want {float(want.flatten()[err.argmax()]):.4f}"
+    # not a trivially-zero result
+    assert float(got.abs().mean()) > 0.1
+
+
+def test_gemm_k_order_and_row_identity():
+    """A = row-selector, W = distinct rows: catches swizzle / descriptor-advance mistakes exactly."""
+    from k_diffusion import _native as N_
+    K, N, M = 256, 128, 256
+    a = torch.zeros(M, K, device=DEV, dtype=torch.bfloat16)
+    idx = torch.arange(M, device=DEV) % K
+    a[torch.arange(M, device=DEV), idx] = 1.0
+    w = ((torch.arange(N, device=DEV)[:, None] * 0.5 + torch.arange(K, device=DEV)[None, :] * 0.25) % 61 - 30).to(torch.bfloat16)
+    got = N_.gemm_bf16(a, w).float()
+    want = w.float().T[idx]                   # row m of C = column idx[m] of W^T
+    assert torch.equal(got, want)
+
+
+def _qkv(B, h, w, nh, seed):
+    """qkv [B, h*w, 3*nh*64] bf16 with cosine-normalised q,k (|q| = |k| = sqrt(10)) like the real layer input."""
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    t = torch.randn(B, h * w, 3, nh, 64, device=DEV, generator=g)
+    t[:, :, :2] = t[:, :, :2] / t[:, :, :2].norm(dim=-1, keepdim=True) * 10 ** 0.5
+    return t.to(torch.bfloat16).reshape(B, h * w, 3 * nh * 64)
+
+
+def _ref_attention(qkv, h, w, nh, kind, param, shift):
+    from oracle import kdiff_oracle as O
+    B = qkv.shape[0]
+    q, k, v = qkv.float().cpu().view(B, h, w, 3, nh, 64).unbind(3)
+    if kind == "global":
+        o = O.global_attention(q, k, v)
+    elif kind == "shifted-window":
+        o = O.shifted_window_attention(q, k, v, param, shift)
+    else:
+        o = O.neighborhood_attention(q, k, v, param)
+    return o.reshape(B, h * w, nh * 64)
+
+
+@pytest.mark.parametrize("B,h,w,nh,kind,param,shift", [
+    (2, 16, 16, 2, "shifted-window", 8, 0), (2, 16, 16, 2, "shifted-window", 8, 4), (1, 8, 8, 4, "shifted-window", 8, 4),
+    (3, 64, 64, 2, "shifted-window", 8, 4), (2, 32, 24, 4, "shifted-window", 8, 0),
+    (2, 16, 16, 8, "global", 0, 0), (1, 8, 16, 2, "global", 0, 0), (1, 32, 32, 4, "global", 0, 0), (2, 16, 24, 1, "global", 0, 0)])
+def test_attention_tcgen05_vs_reference(B, h, w, nh, kind, param, shift):
+    from k_diffusion import _native as N_
+    qkv = _qkv(B, h, w, nh, seed=h * w + nh + shift)
+    want = _ref_attention(qkv, h, w, nh, kind, param, shift)
+    slow = N_.attention(qkv, h, w, nh, 64, kind, param, shift, fast=False).float().cpu()
+    fast = N_.attention(qkv, h, w, nh, 64, kind, param, shift, fast=True).float().cpu()
+    # bf16 output (2^-8 relative) + bf16 P inside the tensor-core path
+    for name, got in (("generic", slow), ("tcgen05", fast)):
+        err = (got - want).abs()
+        assert float(err.max()) < 3e-2 and float(err.mean()) < 3e-3, f"{name}: max {float(err.max()):.4f} mean {float(err.mean()):.5f}"
+
+
+def test_attention_generic_fp32_exact():
+    from k_diffusion import _native as N_
+    for kind, param, shift, h, w in (("global", 0, 0, 7, 7), ("shifted-window", 4, 2, 8, 12), ("neighborhood", 7, 0, 9, 12), ("neighborhood", 3, 0, 5, 4)):
+        qkv = _qkv(2, h, w, 2, seed=h + w).float()
+        want = _ref_attention(qkv, h, w, 2, kind, param, shift)
+        got = N_.attention(qkv, h, w, 2, 64, kind, param, shift).cpu()
+        assert float((got - want).abs().max()) < 2e-5, kind
