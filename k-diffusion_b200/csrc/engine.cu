@@ -29,10 +29,12 @@ struct LayerPlan {
   const float *ff_norm_w = nullptr, *up_w = nullptr, *down_w = nullptr;
   bf16 *qkv_wb = nullptr, *out_wb = nullptr, *up_wb = nullptr, *down_wb = nullptr;
   bf16* up_wb_il = nullptr;          // up_proj rows interleaved (value/gate) for the fused GEGLU epilogue
+  int exec_index = 0;                // position in execution order (indexes PosTables::rope)
 };
 
 struct PosTables {
   std::vector<float*> pos;          // per level: [T_l, 2] (y, x)
+  std::vector<float2*> rope;        // per layer (execution order): [T_l, nh, 16] (cos, sin) of the RoPE angles, or nullptr
 };
 
 }  // namespace kdb
@@ -57,6 +59,7 @@ struct KdbModel {
   float* tap_out = nullptr;
   int64_t tap_cap = 0, tap_count = 0;
   int layer_counter = 0;
+  int n_layers = 0;
 };
 
 namespace {
@@ -208,6 +211,32 @@ int ensure_pos(KdbModel* m, int h0, int w0, cudaStream_t st, PosTables** out) {
       w /= 2;
     }
   }
+  // per-layer RoPE tables (freqs are per-layer buffers of the checkpoint)
+  pt.rope.assign(m->n_layers, nullptr);
+  {
+    auto build = [&](const LayerPlan& L, int hl, int wl) -> int {
+      if (L.attn_type == KDB_ATTN_NONE || L.e != 64) return 0;
+      float2* tab = nullptr;
+      int rc = dev_alloc(m, &tab, (size_t)hl * wl * L.nh * 16);
+      if (rc) return rc;
+      rc = launch_rope_table(pt.pos[L.level], L.freqs, tab, hl * wl, L.nh, L.e / 8, st);
+      if (rc) return rc;
+      pt.rope[L.exec_index] = tab;
+      return 0;
+    };
+    const int nl = m->cfg.n_levels;
+    for (int l = 0; l < nl; ++l) {
+      const int hl = h0 >> l, wl = w0 >> l;
+      int rc;
+      if (l < nl - 1) {
+        for (auto& L : m->down[l]) if ((rc = build(L, hl, wl))) return rc;
+        for (auto& L : m->up[l]) if ((rc = build(L, hl, wl))) return rc;
+      } else {
+        for (auto& L : m->mid) if ((rc = build(L, hl, wl))) return rc;
+      }
+    }
+    KDB_CUDA(cudaStreamSynchronize(st));
+  }
   auto ins = m->pos_cache.emplace(key, std::move(pt));
   *out = &ins.first->second;
   return 0;
@@ -296,8 +325,9 @@ int linear<bf16>(const bf16* A, const bf16* W, bf16* C, int64_t M, int N, int K,
 }
 
 template <typename T>
-int run_layer(KdbModel* m, const LayerPlan& L, T* x, int B, int h, int w, const float* pos, const float* cond, int64_t cond_bs,
+int run_layer(KdbModel* m, const LayerPlan& L, T* x, int B, int h, int w, const PosTables* pt, const float* cond, int64_t cond_bs,
               Workspace& ws, cudaStream_t st) {
+  const float* pos = pt->pos[L.level];
   const int64_t Ttok = (int64_t)h * w, M = (int64_t)B * Ttok;
   const int C = L.C;
   T* xn = reinterpret_cast<T*>(ws.xn);
@@ -310,8 +340,20 @@ int run_layer(KdbModel* m, const LayerPlan& L, T* x, int B, int h, int w, const 
   if (L.attn_type != KDB_ATTN_NONE) {
     if ((rc = launch_rmsnorm<T>(x, xn, cond + L.ada_attn, cond_bs, Ttok, M, C, st))) return rc;
     if ((rc = tap<T>(m, tag + ".xn1", xn, M * C, st))) return rc;
-    if ((rc = linear<T>(xn, WSel<T>::qkv(L), qkv, M, 3 * C, C, GemmEpi{}, st))) return rc;
-    if ((rc = launch_qknorm_rope<T>(qkv, pos, L.freqs, L.scale, M, (int)Ttok, L.nh, L.e, st))) return rc;
+    GemmEpi qe;
+    qe.mode = EPI_QKV_ROPE;
+    qe.C = C;
+    qe.nh = L.nh;
+    qe.T_tokens = (int)Ttok;
+    qe.rope = pt->rope[L.exec_index];
+    qe.qk_scale = L.scale;
+    if (std::is_same<T, bf16>::value && L.e == 64 && tc_gemm_supported(M, 3 * C, C, qe)) {
+      // cosine-sim scaling + RoPE fused into the qkv projection's epilogue
+      if ((rc = launch_gemm_tc(reinterpret_cast<const bf16*>(xn), L.qkv_wb, reinterpret_cast<bf16*>(qkv), M, 3 * C, C, qe, st))) return rc;
+    } else {
+      if ((rc = linear<T>(xn, WSel<T>::qkv(L), qkv, M, 3 * C, C, GemmEpi{}, st))) return rc;
+      if ((rc = launch_qknorm_rope<T>(qkv, pos, L.freqs, L.scale, M, (int)Ttok, L.nh, L.e, st))) return rc;
+    }
     if ((rc = tap<T>(m, tag + ".qkv", qkv, M * 3 * C, st))) return rc;
     if ((rc = attention_dispatch<T>(qkv, ao, B, h, w, L.nh, L.e, L.attn_type, L.attn_param, L.shift, st))) return rc;
     if ((rc = tap<T>(m, tag + ".ao", ao, M * C, st))) return rc;
@@ -364,7 +406,7 @@ int forward_impl(KdbModel* m, int B, int H, int W, const float* x, const float* 
   int h = h0, w = w0;
   for (int l = 0; l < n - 1; ++l) {
     for (const LayerPlan& L : m->down[l])
-      if ((rc = run_layer<T>(m, L, cur, B, h, w, pt->pos[l], cond, cond_bs, ws, st))) return rc;
+      if ((rc = run_layer<T>(m, L, cur, B, h, w, pt, cond, cond_bs, ws, st))) return rc;
     if ((rc = tap<T>(m, "L" + std::to_string(l) + ".down", cur, (int64_t)B * h * w * c.width[l], st))) return rc;
     T* mg = reinterpret_cast<T*>(ws.mg);
     if ((rc = launch_merge_gather<T>(cur, mg, B, h, w, c.width[l], st))) return rc;
@@ -376,7 +418,7 @@ int forward_impl(KdbModel* m, int B, int H, int W, const float* x, const float* 
     cur = nxt;
   }
   for (const LayerPlan& L : m->mid)
-    if ((rc = run_layer<T>(m, L, cur, B, h, w, pt->pos[n - 1], cond, cond_bs, ws, st))) return rc;
+    if ((rc = run_layer<T>(m, L, cur, B, h, w, pt, cond, cond_bs, ws, st))) return rc;
   if ((rc = tap<T>(m, "mid", cur, (int64_t)B * h * w * c.width[n - 1], st))) return rc;
   for (int l = n - 2; l >= 0; --l) {
     T* up = reinterpret_cast<T*>(ws.xup[l]);
@@ -392,7 +434,7 @@ int forward_impl(KdbModel* m, int B, int H, int W, const float* x, const float* 
     w *= 2;
     if ((rc = tap<T>(m, "L" + std::to_string(l) + ".split", up, (int64_t)B * h * w * c.width[l], st))) return rc;
     for (const LayerPlan& L : m->up[l])
-      if ((rc = run_layer<T>(m, L, up, B, h, w, pt->pos[l], cond, cond_bs, ws, st))) return rc;
+      if ((rc = run_layer<T>(m, L, up, B, h, w, pt, cond, cond_bs, ws, st))) return rc;
     if ((rc = tap<T>(m, "L" + std::to_string(l) + ".up", up, (int64_t)B * h * w * c.width[l], st))) return rc;
     cur = up;
   }
@@ -468,6 +510,15 @@ int kdb_model_finalize(KdbModel* m, void* stream) {
         return rc;
   }
   m->ada_total = ada;
+  {
+    int k = 0;
+    for (int l = 0; l < n - 1; ++l)
+      for (auto& L : m->down[l]) L.exec_index = k++;
+    for (auto& L : m->mid) L.exec_index = k++;
+    for (int l = n - 2; l >= 0; --l)
+      for (auto& L : m->up[l]) L.exec_index = k++;
+    m->n_layers = k;
+  }
   for (int l = 0; l < n - 1; ++l) {
     GET("merges." + std::to_string(l) + ".proj.weight", &m->merge_w[l], c.width[l + 1], 4 * c.width[l]);
     GET("splits." + std::to_string(l) + ".proj.weight", &m->split_w[l], 4 * c.width[l], c.width[l + 1]);

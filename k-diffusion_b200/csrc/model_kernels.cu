@@ -63,6 +63,10 @@ template <typename T>
 int launch_patch_in(const float* x, const float* sigma, float sigma_data, const float* W, T* out, int B, int C, int H, int Wd, int ph,
                     int pw, int N, cudaStream_t st) {
   KDB_REQUIRE(H % ph == 0 && Wd % pw == 0, KDB_ERR_BAD_SHAPE, "patch_in: %dx%d not divisible by patch %dx%d", H, Wd, ph, pw);
+  {
+    int rc = 0;
+    if (launch_patch_in_tiled<T>(x, sigma, sigma_data, W, out, B, C, H, Wd, ph, pw, N, st, &rc)) return rc;
+  }
   const int64_t tokens = (int64_t)B * (H / ph) * (Wd / pw);
   const int K = ph * pw * C;
   const size_t smem = sizeof(float) * kPiTok * K;
@@ -304,6 +308,27 @@ int launch_qknorm_rope(T* qkv, const float* pos, const float* freqs, const float
 template int launch_qknorm_rope<float>(float*, const float*, const float*, const float*, int64_t, int, int, int, cudaStream_t);
 template int launch_qknorm_rope<bf16>(bf16*, const float*, const float*, const float*, int64_t, int, int, int, cudaStream_t);
 
+__global__ void __launch_bounds__(256) rope_table_kernel(const float* __restrict__ pos, const float* __restrict__ freqs,
+                                                         float2* __restrict__ out, int T_tokens, int nh, int nf) {
+  const int total = T_tokens * nh * 2 * nf;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
+    const int j = i % (2 * nf);
+    const int h = (i / (2 * nf)) % nh;
+    const int t = i / (2 * nf * nh);
+    const float theta = (j < nf ? pos[t * 2] : pos[t * 2 + 1]) * freqs[h * nf + (j < nf ? j : j - nf)];
+    float s, c;
+    sincosf(theta, &s, &c);
+    out[i] = make_float2(c, s);
+  }
+}
+
+int launch_rope_table(const float* pos, const float* freqs, float2* out, int T_tokens, int nh, int nf, cudaStream_t st) {
+  const int total = T_tokens * nh * 2 * nf;
+  rope_table_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(pos, freqs, out, T_tokens, nh, nf);
+  KDB_LAUNCH_CHECK(F_CONVERT, st);
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Generic attention: one warp per (batch, head, query); key set enumerated per attention type.
 // ------------------------------------------------------------------------------------------------
@@ -531,6 +556,10 @@ __global__ void __launch_bounds__(128) patch_out_kernel(const T* __restrict__ to
 template <typename T>
 int launch_patch_out(const T* tokens, const float* norm_scale, const float* W, const float* x_in, const float* sigma, float sigma_data,
                      float* out, int B, int Cout, int H, int Wd, int ph, int pw, int C0, cudaStream_t st) {
+  {
+    int rc = 0;
+    if (launch_patch_out_tiled<T>(tokens, norm_scale, W, x_in, sigma, sigma_data, out, B, Cout, H, Wd, ph, pw, C0, st, &rc)) return rc;
+  }
   const int64_t tok = (int64_t)B * (H / ph) * (Wd / pw);
   const size_t smem = sizeof(float) * 4 * C0;
   KDB_REQUIRE(smem <= 48 * 1024, KDB_ERR_UNSUPPORTED, "patch_out: width %d too large", C0);

@@ -6,13 +6,17 @@
 
 namespace kdb {
 
-enum GemmEpilogue { EPI_STORE = 0, EPI_RESID = 1, EPI_SPLIT_LERP = 2 };
+enum GemmEpilogue { EPI_STORE = 0, EPI_RESID = 1, EPI_SPLIT_LERP = 2, EPI_QKV_ROPE = 3 };
 
 struct GemmEpi {
   int mode = EPI_STORE;
   const void* resid = nullptr;   // EPI_RESID: [M,N] same type as out.  EPI_SPLIT_LERP: skip [B, 2hc, 2wc, C]
   const float* fac = nullptr;    // EPI_SPLIT_LERP: device scalar (TokenSplit.fac)
   int hc = 0, wc = 0, C = 0;     // EPI_SPLIT_LERP: coarse grid and fine channel count (N == 4*C)
+  // EPI_QKV_ROPE (tensor-core path only): cosine-sim scaling + axial RoPE of the q and k thirds (N == 3*C, d_head 64)
+  const float2* rope = nullptr;  // [T_tokens, nh, 16] (cos, sin) of theta
+  const float* qk_scale = nullptr;   // [nh]
+  int nh = 0, T_tokens = 0;
 };
 
 // x [B,C,H,W] fp32 (* c_in(sigma) if sigma_data > 0) -> tokens [B, H/ph, W/pw, N]   (image_transformer_v2.py:586-595,723-724)
@@ -55,6 +59,14 @@ template <typename T>
 int launch_patch_out(const T* tokens, const float* norm_scale, const float* W, const float* x_in, const float* sigma,
                      float sigma_data, float* out, int B, int Cout, int H, int Wd, int ph, int pw, int C0, cudaStream_t st);
 
+// tiled fast variants (patch_kernels.cu); return false when the shape is outside their envelope
+template <typename T>
+bool launch_patch_in_tiled(const float* x, const float* sigma, float sigma_data, const float* W, T* out, int B, int C, int H, int Wd, int ph,
+                           int pw, int N, cudaStream_t st, int* rc);
+template <typename T>
+bool launch_patch_out_tiled(const T* tokens, const float* norm_scale, const float* W, const float* x_in, const float* sigma, float sigma_data,
+                            float* out, int B, int Cout, int H, int Wd, int ph, int pw, int C0, cudaStream_t st, int* rc);
+
 // mapping network + concatenated AdaRMSNorm projections (image_transformer_v2.py:552-581,734-740,166)
 struct CondWeights {
   int mw, depth, dff, n_classes, mcond_dim, ada_total;
@@ -67,6 +79,9 @@ struct CondWeights {
 };
 int launch_conditioning(const CondWeights& w, int rows, const float* sigma, const float* aug, const int64_t* cls, const float* mcond,
                         float* out, int64_t out_stride, cudaStream_t st);
+
+// (cos, sin) table of the axial RoPE angles: out[t, h, j] for j < 2*nf: theta = (j < nf ? pos_y : pos_x)[t] * freqs[h, j % nf]
+int launch_rope_table(const float* pos, const float* freqs, float2* out, int T_tokens, int nh, int nf, cudaStream_t st);
 
 // dtype conversion helpers
 int launch_f32_to_bf16(const float* in, bf16* out, int64_t n, cudaStream_t st);

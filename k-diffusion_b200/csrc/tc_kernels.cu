@@ -1,14 +1,16 @@
-// tc_kernels.cu -- bf16 tensor-core kernels for sm_100a: TMA (SWIZZLE_128B tiles) -> shared memory ->
-// tcgen05.mma (fp32 accumulators in TMEM) -> tcgen05.ld -> fused epilogue.
+// tc_kernels.cu -- bf16 tensor-core GEMM for sm_100a: TMA (SWIZZLE_128B tiles) -> shared memory ->
+// tcgen05.mma (fp32 accumulators in TMEM) -> tcgen05.ld -> fused epilogue -> swizzled shared tile -> TMA store.
 //
-// GEMM:  C[M,N] = A[M,K] W[N,K]^T for every nn.Linear on the token stream (reference
-// image_transformer_v2.py:126-139), epilogues: plain store, +residual (out_proj/down_proj, :396,:493),
-// GEGLU (:89-95, rows of W interleaved 8 value / 8 gate), TokenSplit scatter + lerp (:618-621).
+// C[M,N] = A[M,K] W[N,K]^T for every nn.Linear on the token stream (reference image_transformer_v2.py:126-139).
+// Epilogues: plain store; +residual (out_proj / down_proj, :396,:493; residual tile prefetched by TMA while the main loop
+// runs); GEGLU (:89-95; rows of W interleaved 8 value / 8 gate); cosine-sim scaling + axial RoPE of q and k fused into the
+// qkv projection (:106-114,187-199,245-248; cos/sin from a per-layer table); TokenSplit scatter + lerp (:618-621).
 //
-// Warp roles in a 192-thread CTA: warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator +
-// MMA issuer (one elected lane), warps 2-5 = epilogue (warp w owns TMEM lanes 32*(w%4)..+31).
-// One 128 x BN output tile per CTA; 2-3 CTAs are co-resident per SM so one tile's epilogue overlaps
-// the next tile's loads and MMAs.
+// Warp roles in a 192-thread CTA: warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer (one
+// elected lane), warps 2-5 = epilogue (warp w owns TMEM lanes 32*(w%4)..+31, one accumulator row per thread).
+// One 128 x BN output tile per CTA; 2-3 CTAs are co-resident per SM so one tile's epilogue overlaps the next tile's main loop.
+// Output rows are written to a SWIZZLE_128B staging tile (the freed pipeline stage 0) and leave through one TMA store per
+// 64 columns: fully coalesced, clipped at the M edge by the tensor map.
 #include "tc_common.cuh"
 #include "tc_kernels.cuh"
 
@@ -58,17 +60,22 @@ namespace {
 
 constexpr int BM = 128, BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KiB
+constexpr int SUB_TILE_BYTES = BM * 128;     // one [128 x 64] bf16 output sub-tile
 constexpr int MAX_STAGES = 4;
 
-enum TcEpi { TCE_STORE = 0, TCE_RESID = 1, TCE_GEGLU = 2, TCE_SPLIT = 3 };
+enum TcEpi { TCE_STORE = 0, TCE_RESID = 1, TCE_GEGLU = 2, TCE_SPLIT = 3, TCE_QKV = 4 };
 
 struct TcParams {
   bf16* out;
-  const bf16* resid;     // RESID: [M, N];  SPLIT: skip [B, 2hc, 2wc, Cf]
+  const bf16* resid;     // SPLIT: skip [B, 2hc, 2wc, Cf]
   const float* fac;
   int64_t M;
   int N, K, stages;
   int hc, wc, Cf;
+  // QKV
+  const float2* rope;    // [T, nh, 16]
+  const float* qk_scale; // [nh]
+  int C, nh, T;
 };
 
 // fast erf-GELU: erf via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7, far below bf16 resolution)
@@ -80,22 +87,28 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
   const float erf_abs = 1.f - poly * t * __expf(-z * z);
-  const float erf = copysignf(erf_abs, x);
-  return 0.5f * x * (1.f + erf);
+  return 0.5f * x * (1.f + copysignf(erf_abs, x));
 }
+
+__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUtensorMap tmb,
+                                                      const __grid_constant__ CUtensorMap tmc, const __grid_constant__ CUtensorMap tmr,
                                                       const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int B_STAGE_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  constexpr int NSUB = BN / 64;              // 64-column groups per tile
   constexpr uint32_t IDESC = tc::idesc_bf16(BM, BN);
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)p.stages * STAGE_BYTES);
+  uint8_t* sC = base;                                            // staging tile = pipeline stage 0 once the main loop is done
+  uint8_t* sR = base + (size_t)p.stages * STAGE_BYTES;           // residual tile (RESID only)
+  uint64_t* full = reinterpret_cast<uint64_t*>(sR + (EPI == TCE_RESID ? NSUB * SUB_TILE_BYTES : 0));
   uint64_t* empty = full + MAX_STAGES;
   uint64_t* tmem_full = empty + MAX_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* resid_full = tmem_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resid_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t m0 = (int64_t)blockIdx.y * BM;
@@ -105,11 +118,13 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   if (threadIdx.x == 0) {
     tc::tma_prefetch_desc(&tma);
     tc::tma_prefetch_desc(&tmb);
+    if constexpr (EPI != TCE_SPLIT) tc::tma_prefetch_desc(&tmc);
     for (int s = 0; s < p.stages; ++s) {
       tc::mbar_init(&full[s], 1);
       tc::mbar_init(&empty[s], 1);
     }
     tc::mbar_init(tmem_full, 1);
+    tc::mbar_init(resid_full, 1);
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, BN);
@@ -120,6 +135,11 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
 
   if (warp == 0) {
     if (tc::elect_one()) {
+      if constexpr (EPI == TCE_RESID) {
+        tc::mbar_arrive_expect_tx(resid_full, NSUB * SUB_TILE_BYTES);
+#pragma unroll
+        for (int g = 0; g < NSUB; ++g) tc::tma_load_2d(sR + g * SUB_TILE_BYTES, &tmr, resid_full, n0 + g * 64, (int)m0);
+      }
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % p.stages;
         const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
@@ -148,58 +168,23 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
       tc::umma_commit(tmem_full);
     }
   } else {
-    // ---------------- epilogue: TMEM -> registers -> global
+    // ---------------- epilogue: TMEM -> registers -> (swizzled smem -> TMA store | direct scatter)
     tc::mbar_wait(tmem_full, 0);
     tc::tc_fence_after();
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int64_t m = m0 + row;
-    const bool live = m < p.M;
-    float facv = 0.f;
-    if constexpr (EPI == TCE_SPLIT) facv = __ldg(p.fac);
+    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
+    if constexpr (EPI == TCE_SPLIT) {
+      // TokenSplit: row m = (b, hy, wx) on the coarse grid; 32 columns inside one (nh, nw) quadrant (Cf % 32 == 0)
+      const bool live = m < p.M;
+      const float facv = __ldg(p.fac);
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      float v[32];
-      tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-      if (!live) continue;
-      const int n = n0 + c * 32;
-      if constexpr (EPI == TCE_STORE || EPI == TCE_RESID) {
-        uint4* dst = reinterpret_cast<uint4*>(p.out + m * p.N + n);
-        if constexpr (EPI == TCE_RESID) {
-          const uint4* rs = reinterpret_cast<const uint4*>(p.resid + m * p.N + n);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 r = rs[j];
-            const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              float lo, hi;
-              tc::unpack_bf16x2(rw[t], lo, hi);
-              v[j * 8 + t * 2] += lo;
-              v[j * 8 + t * 2 + 1] += hi;
-            }
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          dst[j] = make_uint4(tc::pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]), tc::pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]),
-                              tc::pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]), tc::pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]));
-      } else if constexpr (EPI == TCE_GEGLU) {
-        // columns [16g, 16g+8) = value rows, [16g+8, 16g+16) = the matching gate rows; output width N/2
-        uint4* dst = reinterpret_cast<uint4*>(p.out + m * (p.N / 2) + n / 2);
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          float o[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float gate = __bfloat162float(__float2bfloat16_rn(gelu_erf_fast(__bfloat162float(__float2bfloat16_rn(v[g * 16 + 8 + j])))));
-            o[j] = __bfloat162float(__float2bfloat16_rn(v[g * 16 + j])) * gate;
-          }
-          dst[g] = make_uint4(tc::pack_bf16x2(o[0], o[1]), tc::pack_bf16x2(o[2], o[3]), tc::pack_bf16x2(o[4], o[5]),
-                              tc::pack_bf16x2(o[6], o[7]));
-        }
-      } else {
-        // TokenSplit: row m = (b, hy, wx) on the coarse grid; 32 columns inside one (nh, nw) quadrant (Cf % 32 == 0)
+      for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        tc::tmem_ld32(taddr + (uint32_t)(c * 32), v);
+        if (!live) continue;
+        const int n = n0 + c * 32;
         const int64_t b = m / ((int64_t)p.hc * p.wc);
         const int r = (int)(m - b * p.hc * p.wc);
         const int hy = r / p.wc, wx = r - hy * p.wc;
@@ -216,7 +201,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
           for (int t = 0; t < 4; ++t) {
             float lo, hi;
             tc::unpack_bf16x2(rw[t], lo, hi);
-            const float e0 = __bfloat162float(__float2bfloat16_rn(v[j * 8 + t * 2])), e1 = __bfloat162float(__float2bfloat16_rn(v[j * 8 + t * 2 + 1]));
+            const float e0 = bf16_round(v[j * 8 + t * 2]), e1 = bf16_round(v[j * 8 + t * 2 + 1]);
             const float d0 = e0 - lo, d1 = e1 - hi;
             const float o0 = (facv < 0.5f) ? fmaf(facv, d0, lo) : e0 - d0 * (1.f - facv);
             const float o1 = (facv < 0.5f) ? fmaf(facv, d1, hi) : e1 - d1 * (1.f - facv);
@@ -224,6 +209,91 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
           }
           dst[j] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
         }
+      }
+    } else {
+      if constexpr (EPI == TCE_RESID) tc::mbar_wait(resid_full, 0);
+#pragma unroll 1
+      for (int g = 0; g < NSUB; ++g) {
+        float v[64];
+        {
+          float t0[32], t1[32];
+          tc::tmem_ld32(taddr + (uint32_t)(g * 64), t0);
+          tc::tmem_ld32(taddr + (uint32_t)(g * 64 + 32), t1);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { v[i] = t0[i]; v[32 + i] = t1[i]; }
+        }
+        if constexpr (EPI == TCE_GEGLU) {
+          // 64 columns = 4 groups of (8 value, 8 gate) -> 32 outputs = chunks 4g..4g+3 of the single output sub-tile
+#pragma unroll
+          for (int gg = 0; gg < 4; ++gg) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = bf16_round(v[gg * 16 + j]) * bf16_round(gelu_erf_fast(bf16_round(v[gg * 16 + 8 + j])));
+            *reinterpret_cast<uint4*>(sC + tc::sw128_offset(row, g * 4 + gg)) =
+                make_uint4(tc::pack_bf16x2(o[0], o[1]), tc::pack_bf16x2(o[2], o[3]), tc::pack_bf16x2(o[4], o[5]), tc::pack_bf16x2(o[6], o[7]));
+          }
+        } else {
+          if constexpr (EPI == TCE_RESID) {
+            const uint8_t* rt = sR + g * SUB_TILE_BYTES;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint4 r4 = *reinterpret_cast<const uint4*>(rt + tc::sw128_offset(row, j));
+              const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                float lo, hi;
+                tc::unpack_bf16x2(rw[t], lo, hi);
+                v[j * 8 + t * 2] += lo;
+                v[j * 8 + t * 2 + 1] += hi;
+              }
+            }
+          }
+          if constexpr (EPI == TCE_QKV) {
+            // this 64-column group is one head of q, k or v (feature order (t nh e), d_head 64)
+            const int n = n0 + g * 64;
+            const int t3 = n / p.C, head = (n - t3 * p.C) >> 6;
+            if (t3 < 2) {
+              float ss = 0.f;
+#pragma unroll
+              for (int i = 0; i < 64; ++i) {
+                v[i] = bf16_round(v[i]);
+                ss = fmaf(v[i], v[i], ss);
+              }
+              const float sc = sqrtf(__ldg(p.qk_scale + head)) * rsqrtf(ss + 1e-6f);
+#pragma unroll
+              for (int i = 0; i < 64; ++i) v[i] = bf16_round(v[i] * sc);
+              const int64_t tok = (m < p.M ? m : 0) % p.T;
+              const float4* tb = reinterpret_cast<const float4*>(p.rope + (tok * p.nh + head) * 16);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 cs = __ldg(tb + i);      // (cos, sin) of theta_{2i}, theta_{2i+1}
+                const float x1a = v[2 * i], x2a = v[16 + 2 * i], x1b = v[2 * i + 1], x2b = v[17 + 2 * i];
+                v[2 * i] = x1a * cs.x - x2a * cs.y;
+                v[16 + 2 * i] = x2a * cs.x + x1a * cs.y;
+                v[2 * i + 1] = x1b * cs.z - x2b * cs.w;
+                v[17 + 2 * i] = x2b * cs.z + x1b * cs.w;
+              }
+            }
+          }
+          uint8_t* ct = sC + g * SUB_TILE_BYTES;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(ct + tc::sw128_offset(row, j)) =
+                make_uint4(tc::pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]), tc::pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]),
+                           tc::pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]), tc::pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]));
+        }
+      }
+      tc::fence_proxy_async();                 // generic-proxy smem writes -> visible to the TMA (async proxy)
+      tc::named_barrier_sync(1, 128);          // the four epilogue warps only
+      if (warp == 2 && tc::elect_one()) {
+        if constexpr (EPI == TCE_GEGLU) {
+          tc::tma_store_2d(&tmc, sC, n0 / 2, (int)m0);
+        } else {
+#pragma unroll
+          for (int g = 0; g < NSUB; ++g) tc::tma_store_2d(&tmc, sC + g * SUB_TILE_BYTES, n0 + g * 64, (int)m0);
+        }
+        tc::tma_store_commit();
+        tc::tma_store_wait_read();             // smem must stay alive until the bulk store has read it
       }
     }
   }
@@ -235,48 +305,58 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   }
 }
 
+int tmap_2d(CUtensorMap* t, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner, uint32_t box_outer) {
+  const uint64_t dims[2] = {inner, outer};
+  const uint64_t strides[1] = {inner * 2};
+  const uint32_t box[2] = {box_inner, box_outer};
+  return make_tmap_bf16(t, base, 2, dims, strides, box);
+}
+
 template <int BN, int EPI>
-int launch_tc(const bf16* A, const bf16* W, const TcParams& p, int64_t n_rows_w, cudaStream_t st) {
-  CUtensorMap ta, tb;
-  {
-    const uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.M};
-    const uint64_t strides[1] = {(uint64_t)p.K * 2};
-    const uint32_t box[2] = {BK, BM};
-    int rc = make_tmap_bf16(&ta, A, 2, dims, strides, box);
-    if (rc) return rc;
+int launch_tc(const bf16* A, const bf16* W, const TcParams& p, cudaStream_t st) {
+  CUtensorMap ta, tb, tcm, tr;
+  int rc;
+  if ((rc = tmap_2d(&ta, A, (uint64_t)p.K, (uint64_t)p.M, BK, BM))) return rc;
+  if ((rc = tmap_2d(&tb, W, (uint64_t)p.K, (uint64_t)p.N, BK, BN))) return rc;
+  const uint64_t n_out = EPI == TCE_GEGLU ? (uint64_t)p.N / 2 : (uint64_t)p.N;
+  if (EPI != TCE_SPLIT) {
+    if ((rc = tmap_2d(&tcm, p.out, n_out, (uint64_t)p.M, 64, BM))) return rc;
+  } else {
+    tcm = ta;
   }
-  {
-    const uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)n_rows_w};
-    const uint64_t strides[1] = {(uint64_t)p.K * 2};
-    const uint32_t box[2] = {BK, BN};
-    int rc = make_tmap_bf16(&tb, W, 2, dims, strides, box);
-    if (rc) return rc;
+  if (EPI == TCE_RESID) {
+    if ((rc = tmap_2d(&tr, p.resid, (uint64_t)p.N, (uint64_t)p.M, 64, BM))) return rc;
+  } else {
+    tr = ta;
   }
-  const size_t smem = (size_t)p.stages * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 256;
+  const size_t smem = (size_t)p.stages * (A_STAGE_BYTES + BN * BK * 2) + (EPI == TCE_RESID ? (BN / 64) * SUB_TILE_BYTES : 0) + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) {
     KDB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   dim3 grid((unsigned)(p.N / BN), (unsigned)ceil_div(p.M, BM));
-  gemm_tc_kernel<BN, EPI><<<grid, 192, smem, st>>>(ta, tb, p);
+  gemm_tc_kernel<BN, EPI><<<grid, 192, smem, st>>>(ta, tb, tcm, tr, p);
   KDB_LAUNCH_CHECK(F_GEMM_TC, st);
   return 0;
 }
 
 template <int EPI>
 int dispatch_bn(const bf16* A, const bf16* W, const TcParams& p, cudaStream_t st) {
-  if (p.N % 128 == 0) return launch_tc<128, EPI>(A, W, p, p.N, st);
-  return launch_tc<64, EPI>(A, W, p, p.N, st);
+  if (p.N % 128 == 0) return launch_tc<128, EPI>(A, W, p, st);
+  return launch_tc<64, EPI>(A, W, p, st);
 }
 
 bool shape_ok(int64_t M, int N, int K) {
   return M > 0 && M < (65535LL * BM) && N >= 64 && N % 64 == 0 && K >= 64 && K % 64 == 0;
 }
 
-int pick_stages(int K) {
+// stage 0 doubles as the output staging tile, so >= 2 stages keep the tile inside it; the residual variant keeps the CTA
+// under ~100 KB so two CTAs stay co-resident per SM
+int pick_stages(int K, bool resid) {
   const int nkb = K / BK;
-  return nkb < 3 ? nkb : 3;
+  const int want = resid ? 2 : 3;
+  return nkb < want ? (nkb < 1 ? 1 : nkb) : want;
 }
 
 }  // namespace
@@ -289,6 +369,7 @@ static bool g_tc_disabled = [] {
 bool tc_gemm_supported(int64_t M, int N, int K, const GemmEpi& epi) {
   if (g_tc_disabled || !shape_ok(M, N, K)) return false;
   if (epi.mode == EPI_SPLIT_LERP) return epi.C % 32 == 0 && N == 4 * epi.C;
+  if (epi.mode == EPI_QKV_ROPE) return N == 3 * epi.C && epi.C % 64 == 0 && epi.nh * 64 == epi.C && epi.rope != nullptr;
   return epi.mode == EPI_STORE || epi.mode == EPI_RESID;
 }
 
@@ -301,7 +382,7 @@ int launch_gemm_tc(const bf16* A, const bf16* W, bf16* C, int64_t M, int N, int 
   p.M = M;
   p.N = N;
   p.K = K;
-  p.stages = pick_stages(K);
+  p.stages = pick_stages(K, epi.mode == EPI_RESID);
   switch (epi.mode) {
     case EPI_STORE:
       return dispatch_bn<TCE_STORE>(A, W, p, st);
@@ -315,22 +396,29 @@ int launch_gemm_tc(const bf16* A, const bf16* W, bf16* C, int64_t M, int N, int 
       p.wc = epi.wc;
       p.Cf = epi.C;
       return dispatch_bn<TCE_SPLIT>(A, W, p, st);
+    case EPI_QKV_ROPE:
+      p.rope = epi.rope;
+      p.qk_scale = epi.qk_scale;
+      p.C = epi.C;
+      p.nh = epi.nh;
+      p.T = epi.T_tokens;
+      return dispatch_bn<TCE_QKV>(A, W, p, st);
     default:
       KDB_REQUIRE(false, KDB_ERR_BAD_ARG, "gemm_tc: bad epilogue");
   }
 }
 
-bool tc_gemm_geglu_supported(int64_t M, int N2, int K) { return !g_tc_disabled && shape_ok(M, N2, K); }
+bool tc_gemm_geglu_supported(int64_t M, int N2, int K) { return !g_tc_disabled && shape_ok(M, N2, K) && N2 % 128 == 0; }
 
 int launch_gemm_tc_geglu(const bf16* A, const bf16* W_il, bf16* out, int64_t M, int N2, int K, cudaStream_t st) {
-  KDB_REQUIRE(shape_ok(M, N2, K), KDB_ERR_BAD_SHAPE, "gemm_tc_geglu: unsupported shape");
+  KDB_REQUIRE(shape_ok(M, N2, K) && N2 % 128 == 0, KDB_ERR_BAD_SHAPE, "gemm_tc_geglu: unsupported shape");
   TcParams p{};
   p.out = out;
   p.M = M;
   p.N = N2;
   p.K = K;
-  p.stages = pick_stages(K);
-  return dispatch_bn<TCE_GEGLU>(A, W_il, p, st);
+  p.stages = pick_stages(K, false);
+  return launch_tc<128, TCE_GEGLU>(A, W_il, p, st);
 }
 
 }  // namespace kdb
