@@ -101,9 +101,79 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const T* __restrict__ x, T
   for (int c = lane; c < C; c += 32) yr[c] = from_f<T>(to_f(xr[c]) * (__ldg(sc + c) * rstd));
 }
 
+// bf16 fast variant: 16-byte loads/stores, G lanes per row (G = 16 or 32), CH chunks of 8 channels per lane, row kept in registers
+template <int G, int CH>
+__global__ void __launch_bounds__(256) rmsnorm_bf16_vec_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const float* __restrict__ scale,
+                                                               int64_t scale_bstride, int64_t rows_per_batch, int64_t rows) {
+  constexpr int C = G * CH * 8;
+  constexpr int ROWS_PER_WARP = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_id = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t row = warp_id * ROWS_PER_WARP + lane / G;
+  const int sub = lane % G;
+  const bool live = row < rows;
+  float v[CH][8];
+  float ss = 0.f;
+#pragma unroll
+  for (int ch = 0; ch < CH; ++ch) {
+    uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+    if (live) raw = __ldg(reinterpret_cast<const uint4*>(x + row * C + (sub + ch * G) * 8));
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[t]);
+      v[ch][2 * t] = __low2float(h);
+      v[ch][2 * t + 1] = __high2float(h);
+      ss = fmaf(v[ch][2 * t], v[ch][2 * t], ss);
+      ss = fmaf(v[ch][2 * t + 1], v[ch][2 * t + 1], ss);
+    }
+  }
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (!live) return;
+  const float rstd = rsqrtf(ss / (float)C + kEps);
+  const float* sc = scale + (row / rows_per_batch) * scale_bstride;
+#pragma unroll
+  for (int ch = 0; ch < CH; ++ch) {
+    const int c0 = (sub + ch * G) * 8;
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(sc + c0)), s1 = __ldg(reinterpret_cast<const float4*>(sc + c0 + 4));
+    const float s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(v[ch][2 * t] * (s[2 * t] * rstd), v[ch][2 * t + 1] * (s[2 * t + 1] * rstd));
+      o[t] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(y + row * C + c0) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+template <typename T>
+bool rmsnorm_fast(const T*, T*, const float*, int64_t, int64_t, int64_t, int, cudaStream_t) { return false; }
+template <>
+bool rmsnorm_fast<bf16>(const bf16* x, bf16* y, const float* scale, int64_t bs, int64_t rpb, int64_t rows, int C, cudaStream_t st) {
+  if ((reinterpret_cast<uintptr_t>(scale) & 15) != 0 || (bs % 4) != 0) return false;
+#define KDB_RMS(G_, CH_)                                                                                              \
+  rmsnorm_bf16_vec_kernel<G_, CH_><<<(unsigned)ceil_div(rows, 8 * (32 / G_)), 256, 0, st>>>(x, y, scale, bs, rpb, rows); \
+  return true;
+  switch (C) {
+    case 128: KDB_RMS(16, 1)
+    case 256: KDB_RMS(32, 1)
+    case 512: KDB_RMS(32, 2)
+    case 768: KDB_RMS(32, 3)
+    case 1024: KDB_RMS(32, 4)
+    default: return false;
+  }
+#undef KDB_RMS
+}
+
 template <typename T>
 int launch_rmsnorm(const T* x, T* y, const float* scale, int64_t scale_bstride, int64_t rows_per_batch, int64_t rows, int C,
                    cudaStream_t st) {
+  if (rmsnorm_fast<T>(x, y, scale, scale_bstride, rows_per_batch, rows, C, st)) {
+    KDB_LAUNCH_CHECK(F_RMSNORM, st);
+    return 0;
+  }
   rmsnorm_kernel<T><<<(unsigned)ceil_div(rows, 8), 256, 0, st>>>(x, y, scale, scale_bstride, rows_per_batch, rows, C);
   KDB_LAUNCH_CHECK(F_RMSNORM, st);
   return 0;

@@ -1,0 +1,312 @@
+// tc_gemm_persist.cuh -- persistent, warp-specialised tcgen05 GEMM (included inside tc_kernels.cu's anonymous namespace).
+//
+// One CTA per SM loops over 128 x 128 output tiles (tile i -> m-block i / n_tiles, n-block i % n_tiles, so the CTAs of one
+// wave share A blocks in L2).  Nothing of a tile's fixed latency is on the critical path:
+//   warp 0      TMA producer: a STAGES-deep ring of SWIZZLE_128B stages that runs ahead across tiles; also fetches the
+//               residual tile of the tile it is loading for.
+//   warp 1      MMA issuer: tcgen05.mma into one of TWO TMEM accumulators (2 x 128 columns), commit -> frees the stage;
+//               after the last k-block commit -> tmem_full[acc].
+//   warps 2-9   epilogue (256 threads): warp w drains TMEM lanes 32*(w%4).., columns 64*((w-2)/4)..; releases the
+//               accumulator (tmem_empty[acc]) as soon as it is in registers, applies the fused epilogue, writes the row
+//               chunk into a swizzled staging tile, and one thread issues the TMA store.
+// Steady state per tile = max(TMA, MMA, epilogue) instead of their sum.
+//
+// Weight-resident mode (K <= 384): the skinny-K GEMMs of the high-resolution levels are bound by L2->SM operand traffic,
+// not by the tensor pipe (every 128x128 tile would re-fetch a 32 KB weight tile).  The grid is rounded to a multiple of
+// the number of n-blocks, so `tile += gridDim.x` keeps every CTA on ONE n-block; its [128 x K] weight block is loaded
+// once and stays in shared memory, and the ring streams A tiles only (half the bytes per tile, twice the stages).
+#pragma once
+
+constexpr int P_BN = 128;
+constexpr int P_EPI_WARPS = 8;
+constexpr int P_THREADS = 64 + 32 * P_EPI_WARPS;
+constexpr int P_B_TILE_BYTES = P_BN * BK * 2;                     // 16 KiB: one k-block of the weight block
+constexpr int P_OUT_BYTES = 2 * SUB_TILE_BYTES;                   // 128 x 128 bf16 staging tile
+constexpr int P_MAX_STAGES = 8;
+constexpr size_t P_SMEM_LIMIT = 227 * 1024;
+
+struct PersistBars {
+  uint64_t full[P_MAX_STAGES], empty[P_MAX_STAGES];
+  uint64_t tmem_full[2], tmem_empty[2];
+  uint64_t resid_full, resid_empty, b_full;
+  uint32_t tmem;
+};
+
+struct PersistCfg {
+  int stages, b_res, sc_bufs;
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUtensorMap tmb,
+                                                                const __grid_constant__ CUtensorMap tmc, const __grid_constant__ CUtensorMap tmr,
+                                                                const TcParams p, const PersistCfg cfg) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr uint32_t IDESC = tc::idesc_bf16(BM, P_BN);
+  constexpr bool RES = EPI == TCE_RESID;
+  const int nkb = p.K / BK;
+  const int stage_bytes = cfg.b_res ? A_STAGE_BYTES : A_STAGE_BYTES + P_B_TILE_BYTES;
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sB = base;                                                            // resident weight block (b_res)
+  uint8_t* sStage = sB + (cfg.b_res ? (size_t)nkb * P_B_TILE_BYTES : 0);
+  uint8_t* sC = sStage + (size_t)cfg.stages * stage_bytes;                       // 1 or 2 staging tiles
+  uint8_t* sR = sC + (size_t)cfg.sc_bufs * P_OUT_BYTES;                          // residual tile (RESID only)
+  PersistBars* bars = reinterpret_cast<PersistBars*>(sR + (RES ? P_OUT_BYTES : 0));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles_n = p.N / P_BN;
+  const int n_tiles = n_tiles_n * (int)((p.M + BM - 1) / BM);
+
+  if (threadIdx.x == 0) {
+    tc::tma_prefetch_desc(&tma);
+    tc::tma_prefetch_desc(&tmb);
+    tc::tma_prefetch_desc(&tmc);
+    if (RES) tc::tma_prefetch_desc(&tmr);
+    for (int s = 0; s < cfg.stages; ++s) {
+      tc::mbar_init(&bars->full[s], 1);
+      tc::mbar_init(&bars->empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      tc::mbar_init(&bars->tmem_full[a], 1);
+      tc::mbar_init(&bars->tmem_empty[a], 32 * P_EPI_WARPS);
+    }
+    tc::mbar_init(&bars->resid_full, 1);
+    tc::mbar_init(&bars->resid_empty, 1);
+    tc::mbar_init(&bars->b_full, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(&bars->tmem, 2 * P_BN);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = bars->tmem;
+
+  if (warp == 0) {
+    if (tc::elect_one()) {
+      if (cfg.b_res && (int)blockIdx.x < n_tiles) {       // this CTA's n-block never changes (gridDim.x % n_tiles_n == 0)
+        const int n0 = ((int)blockIdx.x % n_tiles_n) * P_BN;
+        tc::mbar_arrive_expect_tx(&bars->b_full, (uint32_t)nkb * P_B_TILE_BYTES);
+        for (int kb = 0; kb < nkb; ++kb) tc::tma_load_2d(sB + (size_t)kb * P_B_TILE_BYTES, &tmb, &bars->b_full, kb * BK, n0);
+      }
+      uint32_t kc = 0, it = 0;      // k-blocks issued so far (ring position), tiles so far
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int m0 = (tile / n_tiles_n) * BM, n0 = (tile % n_tiles_n) * P_BN;
+        for (int kb = 0; kb < nkb; ++kb, ++kc) {
+          const uint32_t s = kc % (uint32_t)cfg.stages, ph = (kc / (uint32_t)cfg.stages) & 1u;
+          tc::mbar_wait(&bars->empty[s], ph ^ 1u);
+          tc::mbar_arrive_expect_tx(&bars->full[s], (uint32_t)stage_bytes);
+          uint8_t* a = sStage + (size_t)s * stage_bytes;
+          tc::tma_load_2d(a, &tma, &bars->full[s], kb * BK, m0);
+          if (!cfg.b_res) tc::tma_load_2d(a + A_STAGE_BYTES, &tmb, &bars->full[s], kb * BK, n0);
+        }
+        if (RES) {   // needed only by this tile's epilogue: issued after the operands so it never delays the MMA
+          tc::mbar_wait(&bars->resid_empty, (it & 1u) ^ 1u);
+          tc::mbar_arrive_expect_tx(&bars->resid_full, P_OUT_BYTES);
+          tc::tma_load_2d(sR, &tmr, &bars->resid_full, n0, m0);
+          tc::tma_load_2d(sR + SUB_TILE_BYTES, &tmr, &bars->resid_full, n0 + 64, m0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (tc::elect_one()) {
+      uint32_t kc = 0, it = 0;
+      if (cfg.b_res && (int)blockIdx.x < n_tiles) tc::mbar_wait(&bars->b_full, 0);
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t acc = it & 1u, use = it >> 1;                // use-th time this accumulator is filled
+        tc::mbar_wait(&bars->tmem_empty[acc], (use & 1u) ^ 1u);     // epilogue drained it
+        tc::tc_fence_after();
+        const uint32_t d = tmem + acc * P_BN;
+        for (int kb = 0; kb < nkb; ++kb, ++kc) {
+          const uint32_t s = kc % (uint32_t)cfg.stages, ph = (kc / (uint32_t)cfg.stages) & 1u;
+          tc::mbar_wait(&bars->full[s], ph);
+          tc::tc_fence_after();
+          const uint32_t a_addr = tc::smem_u32(sStage + (size_t)s * stage_bytes);
+          const uint32_t b_addr = cfg.b_res ? tc::smem_u32(sB + (size_t)kb * P_B_TILE_BYTES) : a_addr + A_STAGE_BYTES;
+          const uint64_t adesc = tc::smem_desc_k_sw128(a_addr);
+          const uint64_t bdesc = tc::smem_desc_k_sw128(b_addr);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) tc::umma_bf16(d, adesc + 2ull * k, bdesc + 2ull * k, IDESC, (uint32_t)((kb | k) != 0));
+          tc::umma_commit(&bars->empty[s]);
+        }
+        tc::umma_commit(&bars->tmem_full[acc]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int ew = warp - 2;                 // 0..7
+    const int q = warp & 3;                  // TMEM lane quadrant this warp may touch
+    const int g = ew >> 2;                   // 64-column group
+    const int row = q * 32 + lane;
+    const bool issuer = (warp == 2);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int m0 = (tile / n_tiles_n) * BM, n0 = (tile % n_tiles_n) * P_BN;
+      const int64_t m = (int64_t)m0 + row;
+      const uint32_t acc = it & 1u, use = it >> 1;
+      uint8_t* ct = sC + (cfg.sc_bufs == 2 ? (size_t)(it & 1u) * P_OUT_BYTES : 0);
+      // the staging tile was last used by tile it-2 (or it-1): its TMA store must have finished READING shared memory
+      if (issuer && lane == 0) {
+        if (cfg.sc_bufs == 2) tc::tma_store_wait_read_le1();
+        else tc::tma_store_wait_read();
+      }
+      tc::named_barrier_sync(1, 32 * P_EPI_WARPS);
+      tc::mbar_wait(&bars->tmem_full[acc], use & 1u);
+      tc::tc_fence_after();
+      float v[64];
+      {
+        uint32_t r0[32], r1[32];
+        const uint32_t taddr = tmem + acc * P_BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 64);
+        tc::tmem_ld32_nowait(taddr, r0);
+        tc::tmem_ld32_nowait(taddr + 32, r1);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { v[i] = __uint_as_float(r0[i]); v[32 + i] = __uint_as_float(r1[i]); }
+      }
+      tc::tc_fence_before();
+      tc::mbar_arrive(&bars->tmem_empty[acc]);          // accumulator is in registers: the MMA warp may refill it
+
+      // Epilogue arithmetic stays in fp32 and is rounded to bf16 once, at the pack (a K=128 tile leaves ~4 ALU
+      // instructions per output element before the epilogue, not the tensor pipe, sets the pace).
+      if constexpr (EPI == TCE_GEGLU) {
+#pragma unroll
+        for (int gg = 0; gg < 4; ++gg) {
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = v[gg * 16 + j] * tc::gelu_fast(v[gg * 16 + 8 + j]);
+          *reinterpret_cast<uint4*>(ct + tc::sw128_offset(row, g * 4 + gg)) =
+              make_uint4(tc::pack_bf16x2(o[0], o[1]), tc::pack_bf16x2(o[2], o[3]), tc::pack_bf16x2(o[4], o[5]), tc::pack_bf16x2(o[6], o[7]));
+        }
+      } else {
+        if constexpr (RES) {
+          tc::mbar_wait(&bars->resid_full, it & 1u);
+          const uint8_t* rt = sR + g * SUB_TILE_BYTES;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint4 r4 = *reinterpret_cast<const uint4*>(rt + tc::sw128_offset(row, j));
+            const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {      // bf16 -> fp32 is a shift / mask
+              v[j * 8 + t * 2] += __uint_as_float(rw[t] << 16);
+              v[j * 8 + t * 2 + 1] += __uint_as_float(rw[t] & 0xffff0000u);
+            }
+          }
+        }
+        if constexpr (EPI == TCE_QKV) {
+          const int n = n0 + g * 64;               // one head of q, k or v (feature order (t nh e), d_head 64)
+          const int t3 = n / p.C, head = (n - t3 * p.C) >> 6;
+          if (t3 < 2) {
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 64; i += 4) {
+              s0 = fmaf(v[i], v[i], s0);
+              s1 = fmaf(v[i + 1], v[i + 1], s1);
+              s2 = fmaf(v[i + 2], v[i + 2], s2);
+              s3 = fmaf(v[i + 3], v[i + 3], s3);
+            }
+            const float sc = sqrtf(__ldg(p.qk_scale + head)) * rsqrtf((s0 + s1) + (s2 + s3) + 1e-6f);
+            const int64_t tok = (m < p.M ? m : 0) % p.T;
+            const float4* tb = reinterpret_cast<const float4*>(p.rope + (tok * p.nh + head) * 16);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 cs = __ldg(tb + i);
+              const float x1a = v[2 * i] * sc, x2a = v[16 + 2 * i] * sc, x1b = v[2 * i + 1] * sc, x2b = v[17 + 2 * i] * sc;
+              v[2 * i] = x1a * cs.x - x2a * cs.y;
+              v[16 + 2 * i] = x2a * cs.x + x1a * cs.y;
+              v[2 * i + 1] = x1b * cs.z - x2b * cs.w;
+              v[17 + 2 * i] = x2b * cs.z + x1b * cs.w;
+            }
+#pragma unroll
+            for (int i = 32; i < 64; ++i) v[i] *= sc;
+          }
+        }
+        uint8_t* cg = ct + g * SUB_TILE_BYTES;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(cg + tc::sw128_offset(row, j)) =
+              make_uint4(tc::pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]), tc::pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]),
+                         tc::pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]), tc::pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]));
+      }
+      tc::fence_proxy_async();
+      tc::named_barrier_sync(2, 32 * P_EPI_WARPS);
+      if (issuer && lane == 0) {
+        if constexpr (RES) tc::mbar_arrive(&bars->resid_empty);      // everyone has consumed the residual tile
+        if constexpr (EPI == TCE_GEGLU) {
+          tc::tma_store_2d(&tmc, ct, n0 / 2, m0);
+        } else {
+          tc::tma_store_2d(&tmc, ct, n0, m0);
+          tc::tma_store_2d(&tmc, ct + SUB_TILE_BYTES, n0 + 64, m0);
+        }
+        tc::tma_store_commit();
+      }
+    }
+    if (issuer && lane == 0) tc::tma_store_wait_read();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem, 2 * P_BN);
+  }
+}
+
+inline int num_sms() {
+  static int n = [] {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = kNumSMs;
+    return v;
+  }();
+  return n;
+}
+
+inline size_t persist_smem(int nkb, bool resid, const PersistCfg& c) {
+  const size_t stage = c.b_res ? A_STAGE_BYTES : A_STAGE_BYTES + P_B_TILE_BYTES;
+  return (c.b_res ? (size_t)nkb * P_B_TILE_BYTES : 0) + (size_t)c.stages * stage + (size_t)c.sc_bufs * P_OUT_BYTES + (resid ? P_OUT_BYTES : 0) +
+         sizeof(PersistBars) + 1024;
+}
+
+// weight-resident when the [128 x K] block plus a >= 3-deep A ring fits; otherwise stream both operands
+inline PersistCfg persist_config(int K, int n_tiles_n, bool resid, bool allow_bres) {
+  static const bool no_bres = [] {
+    const char* e = getenv("KDB200_GEMM_NO_BRES");
+    return e != nullptr && e[0] == '1';
+  }();
+  const int nkb = K / BK;
+  if (allow_bres && !no_bres && nkb <= 6 && n_tiles_n <= num_sms()) {
+    for (int sc = 2; sc >= 1; --sc)
+      for (int st = 6; st >= 3; --st) {
+        PersistCfg c{st, 1, sc};
+        if (persist_smem(nkb, resid, c) <= P_SMEM_LIMIT) return c;
+      }
+  }
+  PersistCfg c{resid ? 3 : 4, 0, 2};
+  return c;
+}
+
+template <int EPI>
+int launch_persist(const bf16* A, const bf16* W, TcParams p, cudaStream_t st) {
+  CUtensorMap ta, tb, tcm, tr;
+  int rc;
+  if ((rc = tmap_2d(&ta, A, (uint64_t)p.K, (uint64_t)p.M, BK, BM))) return rc;
+  if ((rc = tmap_2d(&tb, W, (uint64_t)p.K, (uint64_t)p.N, BK, P_BN))) return rc;
+  const uint64_t n_out = EPI == TCE_GEGLU ? (uint64_t)p.N / 2 : (uint64_t)p.N;
+  if ((rc = tmap_2d(&tcm, p.out, n_out, (uint64_t)p.M, 64, BM))) return rc;
+  if (EPI == TCE_RESID) {
+    if ((rc = tmap_2d(&tr, p.resid, (uint64_t)p.N, (uint64_t)p.M, 64, BM))) return rc;
+  } else {
+    tr = ta;
+  }
+  const int n_tiles_n = p.N / P_BN;
+  const PersistCfg cfg = persist_config(p.K, n_tiles_n, EPI == TCE_RESID, EPI != TCE_QKV);   // q/k tiles are heavier than v tiles: keep the dynamic order
+  p.stages = cfg.stages;
+  const size_t smem = persist_smem(p.K / BK, EPI == TCE_RESID, cfg);
+  static bool attr_set = false;
+  if (!attr_set) {
+    KDB_CUDA(cudaFuncSetAttribute(gemm_tc_persist<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM_LIMIT));
+    attr_set = true;
+  }
+  const int64_t tiles = (int64_t)n_tiles_n * ceil_div(p.M, BM);
+  int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  if (cfg.b_res && tiles > n_tiles_n) grid = grid / n_tiles_n * n_tiles_n;      // keep every CTA on one n-block
+  gemm_tc_persist<EPI><<<grid, P_THREADS, smem, st>>>(ta, tb, tcm, tr, p, cfg);
+  KDB_LAUNCH_CHECK(F_GEMM_TC, st);
+  return 0;
+}

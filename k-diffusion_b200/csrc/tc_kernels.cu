@@ -92,6 +92,13 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
 
 __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
+int tmap_2d(CUtensorMap* t, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner, uint32_t box_outer) {
+  const uint64_t dims[2] = {inner, outer};
+  const uint64_t strides[1] = {inner * 2};
+  const uint32_t box[2] = {box_inner, box_outer};
+  return make_tmap_bf16(t, base, 2, dims, strides, box);
+}
+
 template <int BN, int EPI>
 __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUtensorMap tmb,
                                                       const __grid_constant__ CUtensorMap tmc, const __grid_constant__ CUtensorMap tmr,
@@ -305,11 +312,14 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   }
 }
 
-int tmap_2d(CUtensorMap* t, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner, uint32_t box_outer) {
-  const uint64_t dims[2] = {inner, outer};
-  const uint64_t strides[1] = {inner * 2};
-  const uint32_t box[2] = {box_inner, box_outer};
-  return make_tmap_bf16(t, base, 2, dims, strides, box);
+#include "tc_gemm_persist.cuh"
+
+bool use_persistent(const TcParams& p) {
+  static const bool off = [] {
+    const char* e = getenv("KDB200_GEMM_SIMPLE");
+    return e != nullptr && e[0] == '1';
+  }();
+  return !off && p.N % P_BN == 0;
 }
 
 template <int BN, int EPI>
@@ -343,6 +353,9 @@ int launch_tc(const bf16* A, const bf16* W, const TcParams& p, cudaStream_t st) 
 
 template <int EPI>
 int dispatch_bn(const bf16* A, const bf16* W, const TcParams& p, cudaStream_t st) {
+  if constexpr (EPI != TCE_SPLIT) {
+    if (use_persistent(p)) return launch_persist<EPI>(A, W, p, st);
+  }
   if (p.N % 128 == 0) return launch_tc<128, EPI>(A, W, p, st);
   return launch_tc<64, EPI>(A, W, p, st);
 }
@@ -418,6 +431,7 @@ int launch_gemm_tc_geglu(const bf16* A, const bf16* W_il, bf16* out, int64_t M, 
   p.N = N2;
   p.K = K;
   p.stages = pick_stages(K, false);
+  if (use_persistent(p)) return launch_persist<TCE_GEGLU>(A, W_il, p, st);
   return launch_tc<128, TCE_GEGLU>(A, W_il, p, st);
 }
 

@@ -259,8 +259,7 @@ class _Evaluator:
             self.precision = inner.resolved_precision()
             self.sigma_data = float(model.sigma_data)
             self.per_sample = any(extra_args.get(k) is not None for k in _NATIVE_KW)
-            self.table = None if self.per_sample else self.eng.conditioning(sig)       # one row per evaluation
-            self.static_cond = None
+            self._sig_rows, self.table = sig, None                               # conditioning table: built on first use
 
     def capturable(self):
         return self.native
@@ -272,6 +271,8 @@ class _Evaluator:
             cond = self.inner.conditioning(self.sigma_rows[k], **self.extra_args)
             stride = self.eng.cond_stride
         else:
+            if self.table is None:          # one launch for every evaluation of the schedule (a cached graph never needs it)
+                self.table = self.eng.conditioning(self._sig_rows)
             cond, stride = self.table[k], 0
         return self.eng.forward(x, self.sigma_rows[k], cond, stride, self.sigma_data, self.precision, out=out)
 
