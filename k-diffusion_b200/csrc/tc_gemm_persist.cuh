@@ -28,7 +28,7 @@ constexpr size_t P_SMEM_LIMIT = 227 * 1024;
 struct PersistBars {
   uint64_t full[P_MAX_STAGES], empty[P_MAX_STAGES];
   uint64_t tmem_full[2], tmem_empty[2];
-  uint64_t resid_full, resid_empty, b_full;
+  uint64_t resid_full[2], resid_empty, b_full;   // resid_full per epilogue group: a waiter must observe every phase of its barrier
   uint32_t tmem;
 };
 
@@ -67,9 +67,10 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
     }
     for (int a = 0; a < 2; ++a) {
       tc::mbar_init(&bars->tmem_full[a], 1);
-      tc::mbar_init(&bars->tmem_empty[a], 32 * P_EPI_WARPS);
+      tc::mbar_init(&bars->tmem_empty[a], 128);          // one ping-pong epilogue group (4 warps)
     }
-    tc::mbar_init(&bars->resid_full, 1);
+    tc::mbar_init(&bars->resid_full[0], 1);
+    tc::mbar_init(&bars->resid_full[1], 1);
     tc::mbar_init(&bars->resid_empty, 1);
     tc::mbar_init(&bars->b_full, 1);
     tc::fence_barrier_init();
@@ -100,9 +101,10 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
         }
         if (RES) {   // needed only by this tile's epilogue: issued after the operands so it never delays the MMA
           tc::mbar_wait(&bars->resid_empty, (it & 1u) ^ 1u);
-          tc::mbar_arrive_expect_tx(&bars->resid_full, P_OUT_BYTES);
-          tc::tma_load_2d(sR, &tmr, &bars->resid_full, n0, m0);
-          tc::tma_load_2d(sR + SUB_TILE_BYTES, &tmr, &bars->resid_full, n0 + 64, m0);
+          uint64_t* rf = &bars->resid_full[it & 1u];       // the group that owns tile `it`
+          tc::mbar_arrive_expect_tx(rf, P_OUT_BYTES);
+          tc::tma_load_2d(sR, &tmr, rf, n0, m0);
+          tc::tma_load_2d(sR + SUB_TILE_BYTES, &tmr, rf, n0 + 64, m0);
         }
       }
     }
@@ -131,104 +133,122 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps
+    // ------------------------------------------------------------------ epilogue warps: two ping-pong groups of 4 warps
+    // group grp owns accumulator grp, staging tile grp and every tile with (it & 1) == grp, so one group's TMEM-load /
+    // barrier latency overlaps the other group's arithmetic.  Thread = one accumulator row, two passes of 64 columns.
+    // (Measured: 2 x 8 warps with one pass each is NOT faster -- the tile time is set by the MMA<->epilogue hand-off
+    // latency, not by epilogue issue slots -- and its 96-register cap spills the QKV / residual variants.)
     const int ew = warp - 2;                 // 0..7
+    const int grp = ew >> 2;
     const int q = warp & 3;                  // TMEM lane quadrant this warp may touch
-    const int g = ew >> 2;                   // 64-column group
     const int row = q * 32 + lane;
-    const bool issuer = (warp == 2);
+    const bool issuer = (ew & 3) == 0 && lane == 0;
+    uint8_t* ct = sC + (size_t)grp * P_OUT_BYTES;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      if ((int)(it & 1u) != grp) continue;
       const int m0 = (tile / n_tiles_n) * BM, n0 = (tile % n_tiles_n) * P_BN;
       const int64_t m = (int64_t)m0 + row;
-      const uint32_t acc = it & 1u, use = it >> 1;
-      uint8_t* ct = sC + (cfg.sc_bufs == 2 ? (size_t)(it & 1u) * P_OUT_BYTES : 0);
-      // the staging tile was last used by tile it-2 (or it-1): its TMA store must have finished READING shared memory
-      if (issuer && lane == 0) {
-        if (cfg.sc_bufs == 2) tc::tma_store_wait_read_le1();
-        else tc::tma_store_wait_read();
-      }
-      tc::named_barrier_sync(1, 32 * P_EPI_WARPS);
-      tc::mbar_wait(&bars->tmem_full[acc], use & 1u);
-      tc::tc_fence_after();
-      float v[64];
-      {
-        uint32_t r0[32], r1[32];
-        const uint32_t taddr = tmem + acc * P_BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 64);
-        tc::tmem_ld32_nowait(taddr, r0);
-        tc::tmem_ld32_nowait(taddr + 32, r1);
-        tc::tmem_ld_wait();
+      const uint32_t acc = (uint32_t)grp, use = it >> 1;
+      // QKV: the RoPE table row does not depend on the accumulator -> fetch it before waiting for the MMA
+      float4 cs[2][8];
+      if constexpr (EPI == TCE_QKV) {
+        const int64_t tok = (m < p.M ? m : 0) % p.T;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { v[i] = __uint_as_float(r0[i]); v[32 + i] = __uint_as_float(r1[i]); }
-      }
-      tc::tc_fence_before();
-      tc::mbar_arrive(&bars->tmem_empty[acc]);          // accumulator is in registers: the MMA warp may refill it
-
-      // Epilogue arithmetic stays in fp32 and is rounded to bf16 once, at the pack (a K=128 tile leaves ~4 ALU
-      // instructions per output element before the epilogue, not the tensor pipe, sets the pace).
-      if constexpr (EPI == TCE_GEGLU) {
-#pragma unroll
-        for (int gg = 0; gg < 4; ++gg) {
-          float o[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = v[gg * 16 + j] * tc::gelu_fast(v[gg * 16 + 8 + j]);
-          *reinterpret_cast<uint4*>(ct + tc::sw128_offset(row, g * 4 + gg)) =
-              make_uint4(tc::pack_bf16x2(o[0], o[1]), tc::pack_bf16x2(o[2], o[3]), tc::pack_bf16x2(o[4], o[5]), tc::pack_bf16x2(o[6], o[7]));
-        }
-      } else {
-        if constexpr (RES) {
-          tc::mbar_wait(&bars->resid_full, it & 1u);
-          const uint8_t* rt = sR + g * SUB_TILE_BYTES;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint4 r4 = *reinterpret_cast<const uint4*>(rt + tc::sw128_offset(row, j));
-            const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {      // bf16 -> fp32 is a shift / mask
-              v[j * 8 + t * 2] += __uint_as_float(rw[t] << 16);
-              v[j * 8 + t * 2 + 1] += __uint_as_float(rw[t] & 0xffff0000u);
-            }
-          }
-        }
-        if constexpr (EPI == TCE_QKV) {
-          const int n = n0 + g * 64;               // one head of q, k or v (feature order (t nh e), d_head 64)
+        for (int g = 0; g < 2; ++g) {
+          const int n = n0 + g * 64;
           const int t3 = n / p.C, head = (n - t3 * p.C) >> 6;
           if (t3 < 2) {
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-            for (int i = 0; i < 64; i += 4) {
-              s0 = fmaf(v[i], v[i], s0);
-              s1 = fmaf(v[i + 1], v[i + 1], s1);
-              s2 = fmaf(v[i + 2], v[i + 2], s2);
-              s3 = fmaf(v[i + 3], v[i + 3], s3);
-            }
-            const float sc = sqrtf(__ldg(p.qk_scale + head)) * rsqrtf((s0 + s1) + (s2 + s3) + 1e-6f);
-            const int64_t tok = (m < p.M ? m : 0) % p.T;
             const float4* tb = reinterpret_cast<const float4*>(p.rope + (tok * p.nh + head) * 16);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 cs = __ldg(tb + i);
-              const float x1a = v[2 * i] * sc, x2a = v[16 + 2 * i] * sc, x1b = v[2 * i + 1] * sc, x2b = v[17 + 2 * i] * sc;
-              v[2 * i] = x1a * cs.x - x2a * cs.y;
-              v[16 + 2 * i] = x2a * cs.x + x1a * cs.y;
-              v[2 * i + 1] = x1b * cs.z - x2b * cs.w;
-              v[17 + 2 * i] = x2b * cs.z + x1b * cs.w;
-            }
-#pragma unroll
-            for (int i = 32; i < 64; ++i) v[i] *= sc;
+            for (int i = 0; i < 8; ++i) cs[g][i] = __ldg(tb + i);
           }
         }
-        uint8_t* cg = ct + g * SUB_TILE_BYTES;
+      }
+      if (issuer) tc::tma_store_wait_read();               // this group's previous store has finished READING the staging tile
+      tc::named_barrier_sync(1 + 2 * grp, 128);
+      tc::mbar_wait(&bars->tmem_full[acc], use & 1u);
+      tc::tc_fence_after();
+      if constexpr (RES) tc::mbar_wait(&bars->resid_full[grp], use & 1u);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<uint4*>(cg + tc::sw128_offset(row, j)) =
-              make_uint4(tc::pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]), tc::pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]),
-                         tc::pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]), tc::pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]));
+      for (int g = 0; g < 2; ++g) {
+        float v[64];
+        {
+          uint32_t r0[32], r1[32];
+          const uint32_t taddr = tmem + acc * P_BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 64);
+          tc::tmem_ld32_nowait(taddr, r0);
+          tc::tmem_ld32_nowait(taddr + 32, r1);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { v[i] = __uint_as_float(r0[i]); v[32 + i] = __uint_as_float(r1[i]); }
+        }
+        if (g == 1) {                                      // whole accumulator row is in registers: the MMA warp may refill it
+          tc::tc_fence_before();
+          tc::mbar_arrive(&bars->tmem_empty[acc]);
+        }
+        // Epilogue arithmetic stays in fp32 and is rounded to bf16 once, at the pack (a K=128 tile leaves ~4 ALU
+        // instructions per output element before the epilogue, not the tensor pipe, sets the pace).
+        if constexpr (EPI == TCE_GEGLU) {
+#pragma unroll
+          for (int gg = 0; gg < 4; ++gg) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = v[gg * 16 + j] * tc::gelu_fast(v[gg * 16 + 8 + j]);
+            *reinterpret_cast<uint4*>(ct + tc::sw128_offset(row, g * 4 + gg)) =
+                make_uint4(tc::pack_bf16x2(o[0], o[1]), tc::pack_bf16x2(o[2], o[3]), tc::pack_bf16x2(o[4], o[5]), tc::pack_bf16x2(o[6], o[7]));
+          }
+        } else {
+          if constexpr (RES) {
+            const uint8_t* rt = sR + g * SUB_TILE_BYTES;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint4 r4 = *reinterpret_cast<const uint4*>(rt + tc::sw128_offset(row, j));
+              const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {      // bf16 -> fp32 is a shift / mask
+                v[j * 8 + t * 2] += __uint_as_float(rw[t] << 16);
+                v[j * 8 + t * 2 + 1] += __uint_as_float(rw[t] & 0xffff0000u);
+              }
+            }
+          }
+          if constexpr (EPI == TCE_QKV) {
+            const int n = n0 + g * 64;               // one head of q, k or v (feature order (t nh e), d_head 64)
+            const int t3 = n / p.C, head = (n - t3 * p.C) >> 6;
+            if (t3 < 2) {
+              float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+              for (int i = 0; i < 64; i += 4) {
+                s0 = fmaf(v[i], v[i], s0);
+                s1 = fmaf(v[i + 1], v[i + 1], s1);
+                s2 = fmaf(v[i + 2], v[i + 2], s2);
+                s3 = fmaf(v[i + 3], v[i + 3], s3);
+              }
+              const float sc = sqrtf(__ldg(p.qk_scale + head)) * rsqrtf((s0 + s1) + (s2 + s3) + 1e-6f);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 c4 = cs[g][i];
+                const float x1a = v[2 * i] * sc, x2a = v[16 + 2 * i] * sc, x1b = v[2 * i + 1] * sc, x2b = v[17 + 2 * i] * sc;
+                v[2 * i] = x1a * c4.x - x2a * c4.y;
+                v[16 + 2 * i] = x2a * c4.x + x1a * c4.y;
+                v[2 * i + 1] = x1b * c4.z - x2b * c4.w;
+                v[17 + 2 * i] = x2b * c4.z + x1b * c4.w;
+              }
+#pragma unroll
+              for (int i = 32; i < 64; ++i) v[i] *= sc;
+            }
+          }
+          uint8_t* cg = ct + g * SUB_TILE_BYTES;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(cg + tc::sw128_offset(row, j)) =
+                make_uint4(tc::pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]), tc::pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]),
+                           tc::pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]), tc::pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]));
+        }
       }
       tc::fence_proxy_async();
-      tc::named_barrier_sync(2, 32 * P_EPI_WARPS);
-      if (issuer && lane == 0) {
-        if constexpr (RES) tc::mbar_arrive(&bars->resid_empty);      // everyone has consumed the residual tile
+      tc::named_barrier_sync(2 + 2 * grp, 128);
+      if (issuer) {
+        if constexpr (RES) tc::mbar_arrive(&bars->resid_empty);      // the whole group has consumed the residual tile
         if constexpr (EPI == TCE_GEGLU) {
           tc::tma_store_2d(&tmc, ct, n0 / 2, m0);
         } else {
@@ -238,7 +258,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
         tc::tma_store_commit();
       }
     }
-    if (issuer && lane == 0) tc::tma_store_wait_read();
+    if (issuer) tc::tma_store_wait_read();
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -271,11 +291,10 @@ inline PersistCfg persist_config(int K, int n_tiles_n, bool resid, bool allow_br
   }();
   const int nkb = K / BK;
   if (allow_bres && !no_bres && nkb <= 6 && n_tiles_n <= num_sms()) {
-    for (int sc = 2; sc >= 1; --sc)
-      for (int st = 6; st >= 3; --st) {
-        PersistCfg c{st, 1, sc};
-        if (persist_smem(nkb, resid, c) <= P_SMEM_LIMIT) return c;
-      }
+    for (int st = 6; st >= 3; --st) {
+      PersistCfg c{st, 1, 2};
+      if (persist_smem(nkb, resid, c) <= P_SMEM_LIMIT) return c;
+    }
   }
   PersistCfg c{resid ? 3 : 4, 0, 2};
   return c;
