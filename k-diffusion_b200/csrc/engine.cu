@@ -408,12 +408,23 @@ int forward_impl(KdbModel* m, int B, int H, int W, const float* x, const float* 
     for (const LayerPlan& L : m->down[l])
       if ((rc = run_layer<T>(m, L, cur, B, h, w, pt, cond, cond_bs, ws, st))) return rc;
     if ((rc = tap<T>(m, "L" + std::to_string(l) + ".down", cur, (int64_t)B * h * w * c.width[l], st))) return rc;
-    T* mg = reinterpret_cast<T*>(ws.mg);
-    if ((rc = launch_merge_gather<T>(cur, mg, B, h, w, c.width[l], st))) return rc;
     T* nxt = reinterpret_cast<T*>(ws.xs[l + 1]);
+    GemmEpi me;                      // TokenMerge: the 2x2 gather rides on the GEMM's TMA loads when the geometry allows
+    me.mC = c.width[l];
+    me.mhc = h / 2;
+    me.mwc = w / 2;
+    const int64_t Mc = (int64_t)B * (h / 2) * (w / 2);
+    if (std::is_same<T, bf16>::value && tc_gemm_supported(Mc, c.width[l + 1], 4 * c.width[l], me)) {
+      if ((rc = launch_gemm_tc(reinterpret_cast<const bf16*>(cur), m->merge_wb[l], reinterpret_cast<bf16*>(nxt), Mc, c.width[l + 1], 4 * c.width[l],
+                               me, st)))
+        return rc;
+    } else {
+      T* mg = reinterpret_cast<T*>(ws.mg);
+      if ((rc = launch_merge_gather<T>(cur, mg, B, h, w, c.width[l], st))) return rc;
+      if ((rc = linear<T>(mg, WSel<T>::merge(m, l), nxt, Mc, c.width[l + 1], 4 * c.width[l], GemmEpi{}, st))) return rc;
+    }
     h /= 2;
     w /= 2;
-    if ((rc = linear<T>(mg, WSel<T>::merge(m, l), nxt, (int64_t)B * h * w, c.width[l + 1], 4 * c.width[l], GemmEpi{}, st))) return rc;
     if ((rc = tap<T>(m, "L" + std::to_string(l) + ".merge", nxt, (int64_t)B * h * w * c.width[l + 1], st))) return rc;
     cur = nxt;
   }

@@ -17,6 +17,9 @@ struct GemmEpi {
   const float2* rope = nullptr;  // [T_tokens, nh, 16] (cos, sin) of theta
   const float* qk_scale = nullptr;   // [nh]
   int nh = 0, T_tokens = 0;
+  // TokenMerge folded into the A-operand load (tensor-core path only): A = fine tokens [B, 2*mhc, 2*mwc, mC], K = 4*mC in
+  // (nh nw e) order, M = B*mhc*mwc.  mC == 0 -> A is a plain [M, K] matrix.
+  int mhc = 0, mwc = 0, mC = 0;
 };
 
 // x [B,C,H,W] fp32 (* c_in(sigma) if sigma_data > 0) -> tokens [B, H/ph, W/pw, N]   (image_transformer_v2.py:586-595,723-724)

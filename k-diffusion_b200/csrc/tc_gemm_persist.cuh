@@ -32,6 +32,12 @@ struct PersistBars {
   uint32_t tmem;
 };
 
+// debug timestamps: CTA 0, first 32 tiles, 16 slots per tile
+#define KDB_TRACE(slot_)                                                                          \
+  do {                                                                                            \
+    if (p.trace != nullptr && blockIdx.x == 0 && it < 32) p.trace[it * 16 + (slot_)] = clock64(); \
+  } while (0)
+
 struct PersistCfg {
   int stages, b_res, sc_bufs;
 };
@@ -42,7 +48,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
                                                                 const TcParams p, const PersistCfg cfg) {
   extern __shared__ uint8_t smem_raw[];
   constexpr uint32_t IDESC = tc::idesc_bf16(BM, P_BN);
-  constexpr bool RES = EPI == TCE_RESID;
+  constexpr bool RES = EPI == TCE_RESID || EPI == TCE_SPLIT;   // a second [128 x 128] operand tile (residual / skip) is staged by TMA
   const int nkb = p.K / BK;
   const int stage_bytes = cfg.b_res ? A_STAGE_BYTES : A_STAGE_BYTES + P_B_TILE_BYTES;
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -96,15 +102,28 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
           tc::mbar_wait(&bars->empty[s], ph ^ 1u);
           tc::mbar_arrive_expect_tx(&bars->full[s], (uint32_t)stage_bytes);
           uint8_t* a = sStage + (size_t)s * stage_bytes;
-          tc::tma_load_2d(a, &tma, &bars->full[s], kb * BK, m0);
+          if (p.a_merge) {   // TokenMerge: k-block kb lives in quadrant (nh, nw) of the fine grid, channels e0..e0+63
+            const int qd = (kb * BK) / p.mC, e0 = kb * BK - qd * p.mC;
+            tc::tma_load_5d(a, &tma, &bars->full[s], e0, qd & 1, p.box_h == 1 ? m0 % p.mwc : 0, qd >> 1, m0 / p.mwc);
+          } else {
+            tc::tma_load_2d(a, &tma, &bars->full[s], kb * BK, m0);
+          }
           if (!cfg.b_res) tc::tma_load_2d(a + A_STAGE_BYTES, &tmb, &bars->full[s], kb * BK, n0);
         }
+        KDB_TRACE(0);
         if (RES) {   // needed only by this tile's epilogue: issued after the operands so it never delays the MMA
           tc::mbar_wait(&bars->resid_empty, (it & 1u) ^ 1u);
           uint64_t* rf = &bars->resid_full[it & 1u];       // the group that owns tile `it`
           tc::mbar_arrive_expect_tx(rf, P_OUT_BYTES);
-          tc::tma_load_2d(sR, &tmr, rf, n0, m0);
-          tc::tma_load_2d(sR + SUB_TILE_BYTES, &tmr, rf, n0 + 64, m0);
+          if constexpr (EPI == TCE_SPLIT) {   // skip tensor: fine tokens of quadrant (nh, nw) = n0 / Cf, channels e0..e0+127
+            const int qd = n0 / p.Cf, e0 = n0 - qd * p.Cf;
+            const int wx0 = p.box_h == 1 ? m0 % p.wc : 0, bhy0 = m0 / p.wc;
+            tc::tma_load_5d(sR, &tmr, rf, e0, qd & 1, wx0, qd >> 1, bhy0);
+            tc::tma_load_5d(sR + SUB_TILE_BYTES, &tmr, rf, e0 + 64, qd & 1, wx0, qd >> 1, bhy0);
+          } else {
+            tc::tma_load_2d(sR, &tmr, rf, n0, m0);
+            tc::tma_load_2d(sR + SUB_TILE_BYTES, &tmr, rf, n0 + 64, m0);
+          }
         }
       }
     }
@@ -114,8 +133,10 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
       if (cfg.b_res && (int)blockIdx.x < n_tiles) tc::mbar_wait(&bars->b_full, 0);
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const uint32_t acc = it & 1u, use = it >> 1;                // use-th time this accumulator is filled
+        KDB_TRACE(1);
         tc::mbar_wait(&bars->tmem_empty[acc], (use & 1u) ^ 1u);     // epilogue drained it
         tc::tc_fence_after();
+        KDB_TRACE(2);
         const uint32_t d = tmem + acc * P_BN;
         for (int kb = 0; kb < nkb; ++kb, ++kc) {
           const uint32_t s = kc % (uint32_t)cfg.stages, ph = (kc / (uint32_t)cfg.stages) & 1u;
@@ -130,6 +151,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
           tc::umma_commit(&bars->empty[s]);
         }
         tc::umma_commit(&bars->tmem_full[acc]);
+        KDB_TRACE(3);
       }
     }
   } else {
@@ -144,6 +166,8 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
     const int row = q * 32 + lane;
     const bool issuer = (ew & 3) == 0 && lane == 0;
     uint8_t* ct = sC + (size_t)grp * P_OUT_BYTES;
+    float facv = 0.f;
+    if constexpr (EPI == TCE_SPLIT) facv = __ldg(p.fac);
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       if ((int)(it & 1u) != grp) continue;
@@ -165,10 +189,14 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
           }
         }
       }
+      if (issuer) KDB_TRACE(4);
       if (issuer) tc::tma_store_wait_read();               // this group's previous store has finished READING the staging tile
+      if (issuer) KDB_TRACE(5);
       tc::named_barrier_sync(1 + 2 * grp, 128);
+      if (issuer) KDB_TRACE(6);
       tc::mbar_wait(&bars->tmem_full[acc], use & 1u);
       tc::tc_fence_after();
+      if (issuer) KDB_TRACE(7);
       if constexpr (RES) tc::mbar_wait(&bars->resid_full[grp], use & 1u);
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
@@ -186,6 +214,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
           tc::tc_fence_before();
           tc::mbar_arrive(&bars->tmem_empty[acc]);
         }
+        if (issuer) KDB_TRACE(8 + g);
         // Epilogue arithmetic stays in fp32 and is rounded to bf16 once, at the pack (a K=128 tile leaves ~4 ALU
         // instructions per output element before the epilogue, not the tensor pipe, sets the pace).
         if constexpr (EPI == TCE_GEGLU) {
@@ -206,8 +235,15 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
               const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
               for (int t = 0; t < 4; ++t) {      // bf16 -> fp32 is a shift / mask
-                v[j * 8 + t * 2] += __uint_as_float(rw[t] << 16);
-                v[j * 8 + t * 2 + 1] += __uint_as_float(rw[t] & 0xffff0000u);
+                const float lo = __uint_as_float(rw[t] << 16), hi = __uint_as_float(rw[t] & 0xffff0000u);
+                if constexpr (EPI == TCE_SPLIT) {   // torch.lerp(skip, x, fac) (reference :621)
+                  const float d0 = v[j * 8 + t * 2] - lo, d1 = v[j * 8 + t * 2 + 1] - hi;
+                  v[j * 8 + t * 2] = (facv < 0.5f) ? fmaf(facv, d0, lo) : v[j * 8 + t * 2] - d0 * (1.f - facv);
+                  v[j * 8 + t * 2 + 1] = (facv < 0.5f) ? fmaf(facv, d1, hi) : v[j * 8 + t * 2 + 1] - d1 * (1.f - facv);
+                } else {
+                  v[j * 8 + t * 2] += lo;
+                  v[j * 8 + t * 2 + 1] += hi;
+                }
               }
             }
           }
@@ -245,17 +281,25 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
                            tc::pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]), tc::pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]));
         }
       }
+      if (issuer) KDB_TRACE(10);
       tc::fence_proxy_async();
       tc::named_barrier_sync(2 + 2 * grp, 128);
+      if (issuer) KDB_TRACE(11);
       if (issuer) {
         if constexpr (RES) tc::mbar_arrive(&bars->resid_empty);      // the whole group has consumed the residual tile
         if constexpr (EPI == TCE_GEGLU) {
           tc::tma_store_2d(&tmc, ct, n0 / 2, m0);
+        } else if constexpr (EPI == TCE_SPLIT) {
+          const int qd = n0 / p.Cf, e0 = n0 - qd * p.Cf;
+          const int wx0 = p.box_h == 1 ? m0 % p.wc : 0, bhy0 = m0 / p.wc;
+          tc::tma_store_5d(&tmc, ct, e0, qd & 1, wx0, qd >> 1, bhy0);
+          tc::tma_store_5d(&tmc, ct + SUB_TILE_BYTES, e0 + 64, qd & 1, wx0, qd >> 1, bhy0);
         } else {
           tc::tma_store_2d(&tmc, ct, n0, m0);
           tc::tma_store_2d(&tmc, ct + SUB_TILE_BYTES, n0 + 64, m0);
         }
         tc::tma_store_commit();
+        KDB_TRACE(12);
       }
     }
     if (issuer) tc::tma_store_wait_read();
@@ -304,19 +348,28 @@ template <int EPI>
 int launch_persist(const bf16* A, const bf16* W, TcParams p, cudaStream_t st) {
   CUtensorMap ta, tb, tcm, tr;
   int rc;
-  if ((rc = tmap_2d(&ta, A, (uint64_t)p.K, (uint64_t)p.M, BK, BM))) return rc;
-  if ((rc = tmap_2d(&tb, W, (uint64_t)p.K, (uint64_t)p.N, BK, P_BN))) return rc;
-  const uint64_t n_out = EPI == TCE_GEGLU ? (uint64_t)p.N / 2 : (uint64_t)p.N;
-  if ((rc = tmap_2d(&tcm, p.out, n_out, (uint64_t)p.M, 64, BM))) return rc;
-  if (EPI == TCE_RESID) {
-    if ((rc = tmap_2d(&tr, p.resid, (uint64_t)p.N, (uint64_t)p.M, 64, BM))) return rc;
+  if (p.a_merge) {
+    if ((rc = tmap_quad(&ta, A, p.mC, p.mwc, (uint64_t)p.M / p.mwc, p.box_w, p.box_h))) return rc;
   } else {
-    tr = ta;
+    if ((rc = tmap_2d(&ta, A, (uint64_t)p.K, (uint64_t)p.M, BK, BM))) return rc;
+  }
+  if ((rc = tmap_2d(&tb, W, (uint64_t)p.K, (uint64_t)p.N, BK, P_BN))) return rc;
+  if (EPI == TCE_SPLIT) {
+    if ((rc = tmap_quad(&tcm, p.out, p.Cf, p.wc, (uint64_t)p.M / p.wc, p.box_w, p.box_h))) return rc;
+    if ((rc = tmap_quad(&tr, p.resid, p.Cf, p.wc, (uint64_t)p.M / p.wc, p.box_w, p.box_h))) return rc;
+  } else {
+    const uint64_t n_out = EPI == TCE_GEGLU ? (uint64_t)p.N / 2 : (uint64_t)p.N;
+    if ((rc = tmap_2d(&tcm, p.out, n_out, (uint64_t)p.M, 64, BM))) return rc;
+    if (EPI == TCE_RESID) {
+      if ((rc = tmap_2d(&tr, p.resid, (uint64_t)p.N, (uint64_t)p.M, 64, BM))) return rc;
+    } else {
+      tr = ta;
+    }
   }
   const int n_tiles_n = p.N / P_BN;
-  const PersistCfg cfg = persist_config(p.K, n_tiles_n, EPI == TCE_RESID, EPI != TCE_QKV);   // q/k tiles are heavier than v tiles: keep the dynamic order
+  const PersistCfg cfg = persist_config(p.K, n_tiles_n, EPI == TCE_RESID || EPI == TCE_SPLIT, EPI != TCE_QKV);   // q/k tiles are heavier than v tiles: keep the dynamic order
   p.stages = cfg.stages;
-  const size_t smem = persist_smem(p.K / BK, EPI == TCE_RESID, cfg);
+  const size_t smem = persist_smem(p.K / BK, EPI == TCE_RESID || EPI == TCE_SPLIT, cfg);
   static bool attr_set = false;
   if (!attr_set) {
     KDB_CUDA(cudaFuncSetAttribute(gemm_tc_persist<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM_LIMIT));
@@ -325,7 +378,32 @@ int launch_persist(const bf16* A, const bf16* W, TcParams p, cudaStream_t st) {
   const int64_t tiles = (int64_t)n_tiles_n * ceil_div(p.M, BM);
   int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   if (cfg.b_res && tiles > n_tiles_n) grid = grid / n_tiles_n * n_tiles_n;      // keep every CTA on one n-block
+  static const bool trace_on = [] {
+    const char* e = getenv("KDB200_GEMM_TRACE");
+    return e != nullptr && e[0] == '1';
+  }();
+  static long long* trace_buf = nullptr;
+  if (trace_on) {
+    if (trace_buf == nullptr) KDB_CUDA(cudaMalloc(&trace_buf, 32 * 16 * sizeof(long long)));
+    KDB_CUDA(cudaMemsetAsync(trace_buf, 0, 32 * 16 * sizeof(long long), st));
+    p.trace = trace_buf;
+  }
   gemm_tc_persist<EPI><<<grid, P_THREADS, smem, st>>>(ta, tb, tcm, tr, p, cfg);
   KDB_LAUNCH_CHECK(F_GEMM_TC, st);
+  if (trace_on) {
+    static long long h[32 * 16];
+    KDB_CUDA(cudaMemcpyAsync(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost, st));
+    KDB_CUDA(cudaStreamSynchronize(st));
+    const char* names[13] = {"prod_issued", "mma_pre_empty", "mma_post_empty", "mma_committed", "epi_top", "epi_store_drained", "epi_bar1",
+                             "epi_tmem_full", "epi_pass0", "epi_pass1", "epi_sts_done", "epi_bar2", "epi_store_issued"};
+    fprintf(stderr, "GEMM trace EPI=%d M=%lld N=%d K=%d grid=%d stages=%d b_res=%d (cycles relative to tile 0 mma_pre_empty)\n", EPI, (long long)p.M,
+            p.N, p.K, grid, cfg.stages, cfg.b_res);
+    const long long t0 = h[1];
+    for (int t = 0; t < 12; ++t) {
+      fprintf(stderr, " tile %2d:", t);
+      for (int k = 0; k < 13; ++k) fprintf(stderr, " %s=%lld", names[k], h[t * 16 + k] ? h[t * 16 + k] - t0 : -1);
+      fprintf(stderr, "\n");
+    }
+  }
   return 0;
 }

@@ -76,6 +76,9 @@ struct TcParams {
   const float2* rope;    // [T, nh, 16]
   const float* qk_scale; // [nh]
   int C, nh, T;
+  int a_merge, mwc, mC;  // A operand gathered from fine tokens (TokenMerge): coarse grid width, fine channels
+  int box_w, box_h;      // 5-D TMA boxes of merge / split: 128 rows = box_h x box_w coarse tokens
+  long long* trace;      // debug: per-tile clock64 stamps of CTA 0 (KDB200_GEMM_TRACE=1), else nullptr
 };
 
 // fast erf-GELU: erf via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7, far below bf16 resolution)
@@ -97,6 +100,30 @@ int tmap_2d(CUtensorMap* t, const void* base, uint64_t inner, uint64_t outer, ui
   const uint64_t strides[1] = {inner * 2};
   const uint32_t box[2] = {box_inner, box_outer};
   return make_tmap_bf16(t, base, 2, dims, strides, box);
+}
+
+// 5-D view of a fine token tensor X[B, 2*hc, 2*wc, C] as (e, nw, wx, nh, b*hc+hy): one (nh, nw) quadrant of `box_h x box_w`
+// coarse tokens x 64 channels is a [128 x 64] SWIZZLE_128B tile in coarse-token order -- TokenMerge's gather and TokenSplit's
+// scatter become TMA coordinates (reference image_transformer_v2.py:594,607,620).
+int tmap_quad(CUtensorMap* t, const void* base, int C, int wc, uint64_t bhc, int box_w, int box_h) {
+  const uint64_t dims[5] = {(uint64_t)C, 2, (uint64_t)wc, 2, bhc};
+  const uint64_t strides[4] = {(uint64_t)C * 2, (uint64_t)C * 4, (uint64_t)wc * C * 4, (uint64_t)wc * C * 8};
+  const uint32_t box[5] = {64, 1, (uint32_t)box_w, 1, (uint32_t)box_h};
+  return make_tmap_bf16(t, base, 5, dims, strides, box);
+}
+
+// 128 consecutive coarse tokens as a box_h x box_w rectangle of the coarse grid (rows of width wc)
+bool quad_box(int wc, int* box_w, int* box_h) {
+  if (wc >= BM) {
+    if (wc % BM != 0) return false;
+    *box_w = BM;
+    *box_h = 1;
+    return true;
+  }
+  if (BM % wc != 0) return false;
+  *box_w = wc;
+  *box_h = BM / wc;
+  return true;
 }
 
 template <int BN, int EPI>
@@ -355,6 +382,9 @@ template <int EPI>
 int dispatch_bn(const bf16* A, const bf16* W, const TcParams& p, cudaStream_t st) {
   if constexpr (EPI != TCE_SPLIT) {
     if (use_persistent(p)) return launch_persist<EPI>(A, W, p, st);
+  } else {
+    TcParams q = p;
+    if (use_persistent(p) && p.Cf % P_BN == 0 && p.M % p.wc == 0 && quad_box(p.wc, &q.box_w, &q.box_h)) return launch_persist<EPI>(A, W, q, st);
   }
   if (p.N % 128 == 0) return launch_tc<128, EPI>(A, W, p, st);
   return launch_tc<64, EPI>(A, W, p, st);
@@ -381,6 +411,10 @@ static bool g_tc_disabled = [] {
 
 bool tc_gemm_supported(int64_t M, int N, int K, const GemmEpi& epi) {
   if (g_tc_disabled || !shape_ok(M, N, K)) return false;
+  if (epi.mC > 0) {   // TokenMerge gather folded into the A loads: persistent kernel only, plain store epilogue
+    int bw, bh;
+    if (epi.mode != EPI_STORE || N % 128 != 0 || epi.mC % 64 != 0 || K != 4 * epi.mC || M % epi.mwc != 0 || !quad_box(epi.mwc, &bw, &bh)) return false;
+  }
   if (epi.mode == EPI_SPLIT_LERP) return epi.C % 32 == 0 && N == 4 * epi.C;
   if (epi.mode == EPI_QKV_ROPE) return N == 3 * epi.C && epi.C % 64 == 0 && epi.nh * 64 == epi.C && epi.rope != nullptr;
   return epi.mode == EPI_STORE || epi.mode == EPI_RESID;
@@ -396,6 +430,14 @@ int launch_gemm_tc(const bf16* A, const bf16* W, bf16* C, int64_t M, int N, int 
   p.N = N;
   p.K = K;
   p.stages = pick_stages(K, epi.mode == EPI_RESID);
+  if (epi.mC > 0) {
+    KDB_REQUIRE(tc_gemm_supported(M, N, K, epi), KDB_ERR_UNSUPPORTED, "gemm_tc: token-merge geometry not supported");
+    p.a_merge = 1;
+    p.mC = epi.mC;
+    p.mwc = epi.mwc;
+    quad_box(epi.mwc, &p.box_w, &p.box_h);
+    return launch_persist<TCE_STORE>(A, W, p, st);
+  }
   switch (epi.mode) {
     case EPI_STORE:
       return dispatch_bn<TCE_STORE>(A, W, p, st);
