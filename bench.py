@@ -282,22 +282,50 @@ def main():
         total = sum(t for _, t in prof.by_family.values())
         breakdown = {f: {"launches": c, "ms": round(t, 3), "share": round(t / total, 4)} for f, (c, t) in
                      sorted(prof.by_family.items(), key=lambda kv: -kv[1][1])}
+        # dominant kernel = the tcgen05 GEMM behind every nn.Linear on the token stream (94 % of the model's MACs).
+        # Launches are matched to shapes by execution order (k_diffusion.models.flops.linear_layers).
         gemm_fams = [f for f in prof.by_family if f.startswith("gemm")]
-        g_launch = sum(prof.by_family[f][0] for f in gemm_fams)
-        g_ms = sum(prof.by_family[f][1] for f in gemm_fams)
-        flops = 2.0 * linear_macs_per_image(cfg["model"]) * B * 9
+        g_times = [t for f, t in prof.launches if f.startswith("gemm")]
+        seq = K.models.flops.linear_layers(cfg["model"], B)
+        per_shape = {}
+        for idx, t in enumerate(g_times):
+            label, M_, N_, K_ = seq[idx % len(seq)]
+            key = (label.split(" ", 1)[-1] if " " in label else label.rstrip("0123456789"), M_, N_, K_)
+            c, tot = per_shape.get(key, (0, 0.0))
+            per_shape[key] = (c + 1, tot + t)
+        g_launch, g_ms = len(g_times), sum(g_times)
+        flops = 2.0 * K.models.flops.linear_macs(cfg["model"], B) * (len(g_times) / len(seq))
         peaks_file = ROOT / "MEASURED_PEAKS.json"
         if peaks_file.exists():
             peak, which = json.loads(peaks_file.read_text())["bf16_tflops_sustained"], "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
         else:
             peak, which = 1400.0, "fallback (B200_PROFILING.md sustained 1.4 PFLOP/s)"
         ach = flops / (g_ms / 1000.0) / 1e12
-        roofline = {"bound": "tensor", "kernel": "+".join(sorted(gemm_fams)) + " (all token-stream Linear layers)",
+        shapes = []
+        for (kind, M_, N_, K_), (c, tot) in sorted(per_shape.items(), key=lambda kv: -kv[1][1])[:6]:
+            tf = 2.0 * M_ * N_ * K_ * c / (tot / 1000.0) / 1e12
+            shapes.append({"op": kind, "M": M_, "N": N_, "K": K_, "launches": c, "avg_launch_us": round(1000.0 * tot / c, 2),
+                           "achieved": round(tf, 1), "frac": round(tf / peak, 4), "share_of_step": round(tot / total, 4)})
+        ncu_file = ROOT / "profiles" / "r1_ncu_full_summary.json"
+        traffic, traffic_note = None, "no ncu capture committed"
+        if ncu_file.exists():
+            try:
+                first = next(iter(json.loads(ncu_file.read_text()).values()))[0]
+                traffic = (float(first["dram__bytes_read.sum [Mbyte]"]) + float(first["dram__bytes_write.sum [Mbyte]"])) * 1e6
+                traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the heaviest shape (" + first["launch"] +
+                                "), from the committed ncu --set full capture profiles/r1_ncu_full_summary.json; algorithmic bytes of that "
+                                "launch = A 33.6 MB + W 0.2 MB + out 50.3 MB")
+            except (KeyError, ValueError, StopIteration):
+                pass
+        roofline = {"bound": "tensor", "kernel": "gemm_tc_persist / gemm_tc_kernel (tcgen05 GEMM, all token-stream Linear layers: " +
+                                                 "+".join(sorted(gemm_fams)) + ")",
                     "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4), "peak_source": which,
                     "avg_launch_us": round(1000.0 * g_ms / max(g_launch, 1), 2), "launches": g_launch,
-                    "share_of_step": round(g_ms / total, 4), "traffic": None,
-                    "how": "CUDA events after every launch of one eager sample_heun (5 Karras steps) at the bench batch; "
-                           "algorithmic flops = 2 x Linear MACs (reference flops.py formulas)"}
+                    "share_of_step": round(g_ms / total, 4), "traffic": traffic, "traffic_note": traffic_note, "by_shape": shapes,
+                    "how": "CUDA events after every launch (on the launching stream) of one eager sample_heun with 5 Karras steps at the bench "
+                           "batch; achieved = 2 x Linear MACs of those launches (reference flops.py accounting) / their summed device time",
+                    "note": "the K=128/256 GEMMs of the two high-resolution levels are bound by L2->SM operand bandwidth (A is re-read N/128 "
+                            "times), not by the tensor pipe: see DESIGN.md section 4"}
         if world == 1:
             O, cpu_model, cores = cpu_port_setup()
             v, sample = cpu_port_time(O, cpu_model, 2, args.cpu_seconds)

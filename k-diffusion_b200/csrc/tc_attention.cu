@@ -40,14 +40,16 @@ __device__ __forceinline__ uint32_t p_offset(int row, int chunk16) {   // byte o
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(160) attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, const AttnParams p) {
+__global__ void __launch_bounds__(160, MODE == MODE_WINDOW ? 4 : 2) attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = base;
   uint8_t* sK = base + TILE_BYTES;
   uint8_t* sV = base + 2 * TILE_BYTES;
-  uint8_t* sP = base + 3 * TILE_BYTES;     // two K-blocks of 64 keys: 2 x 16 KiB
-  Bars* bars = reinterpret_cast<Bars*>(base + 5 * TILE_BYTES);
+  // P (two K-blocks of 64 keys, 32 KiB).  WINDOW has a single key block: Q and K are dead once S = Q K^T has completed, so
+  // P overwrites them (48 KiB per CTA -> 3-4 CTAs per SM); GLOBAL re-uses Q for every key block and keeps P separate.
+  uint8_t* sP = (MODE == MODE_WINDOW) ? sQ : base + 3 * TILE_BYTES;
+  Bars* bars = reinterpret_cast<Bars*>(base + (MODE == MODE_WINDOW ? 3 : 5) * TILE_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nh = p.nh;
@@ -75,17 +77,24 @@ __global__ void __launch_bounds__(160) attn_tc_kernel(const __grid_constant__ CU
     tc::mbar_init(&bars->o, 1);
     tc::fence_barrier_init();
   }
-  if (warp == 4) tc::tmem_alloc(&bars->tmem, 256);
+  constexpr uint32_t TMEM_COLS = (MODE == MODE_WINDOW) ? 128 : 256;
+  if (warp == 4) tc::tmem_alloc(&bars->tmem, TMEM_COLS);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_s = bars->tmem;          // columns [0,128): S
-  const uint32_t tmem_o = bars->tmem + 128;    // columns [128,192): O
+  // O: 64 columns.  WINDOW: P V is only issued after every thread has read S (bar_p), so O re-uses S's first columns.
+  const uint32_t tmem_o = bars->tmem + (MODE == MODE_WINDOW ? 0 : 128);
 
   if (warp == 4) {
     if (tc::elect_one()) {
       // ------------------------------------------------ loads of Q (and window K,V)
       auto load_window_tile = [&](uint8_t* dst, int t, uint64_t* bar) {
+        if (p.shift == 0) {   // unshifted window: one 8x8 box per head, rows in (lr, lc) order (tensor map box = 64 x 8 x 8)
+#pragma unroll
+          for (int hd = 0; hd < 2; ++hd) tc::tma_load_4d(dst + hd * 64 * 128, &tmap, bar, (t * nh + head0 + hd) * DH, wj * 8, wi * 8, b);
+          return;
+        }
 #pragma unroll
         for (int hd = 0; hd < 2; ++hd)
 #pragma unroll
@@ -258,9 +267,15 @@ __global__ void __launch_bounds__(160) attn_tc_kernel(const __grid_constant__ CU
     int64_t token;
     int head;
     if constexpr (MODE == MODE_WINDOW) {
-      const int lr = (row & 15) >> 2, lc = row & 3;
-      const int oi = (wi * 8 + (quad >> 1) * 4 + lr - p.shift + p.h) % p.h;
-      const int oj = (wj * 8 + (quad & 1) * 4 + lc - p.shift + p.w) % p.w;
+      int oi, oj;
+      if (p.shift == 0) {
+        oi = wi * 8 + ((row & 63) >> 3);
+        oj = wj * 8 + (row & 7);
+      } else {
+        const int lr = (row & 15) >> 2, lc = row & 3;
+        oi = (wi * 8 + (quad >> 1) * 4 + lr - p.shift + p.h) % p.h;
+        oj = (wj * 8 + (quad & 1) * 4 + lc - p.shift + p.w) % p.w;
+      }
       token = (int64_t)oi * p.w + oj;
       head = head0 + hd;
     } else {
@@ -282,11 +297,12 @@ __global__ void __launch_bounds__(160) attn_tc_kernel(const __grid_constant__ CU
   __syncthreads();
   if (warp == 4) {
     tc::tc_fence_after();
-    tc::tmem_dealloc(bars->tmem, 256);
+    tc::tmem_dealloc(bars->tmem, TMEM_COLS);
   }
 }
 
-constexpr size_t ATTN_SMEM = 5 * TILE_BYTES + 1024 + 128;
+constexpr size_t ATTN_SMEM = 5 * TILE_BYTES + 1024 + 128;          // GLOBAL
+constexpr size_t ATTN_SMEM_WINDOW = 3 * TILE_BYTES + 1024 + 128;   // WINDOW (P aliases Q,K)
 
 }  // namespace
 
@@ -318,16 +334,16 @@ int launch_attention_tc(const bf16* qkv, bf16* out, int B, int h, int w, int nh,
     KDB_REQUIRE(shift == 0 || shift == 4, KDB_ERR_UNSUPPORTED, "attention_tc: window shift must be 0 or window/2");
     const uint64_t dims[4] = {F, (uint64_t)w, (uint64_t)h, (uint64_t)B};
     const uint64_t strides[3] = {F * 2, F * 2 * w, F * 2 * w * h};
-    const uint32_t box[4] = {DH, 4, 4, 1};
-    int rc = make_tmap_bf16(&tm, qkv, 4, dims, strides, box);
+    const uint32_t box_q[4] = {DH, 4, 4, 1}, box_f[4] = {DH, 8, 8, 1};
+    int rc = make_tmap_bf16(&tm, qkv, 4, dims, strides, shift == 0 ? box_f : box_q);
     if (rc) return rc;
     if (!attr_w) {
-      KDB_CUDA(cudaFuncSetAttribute(attn_tc_kernel<MODE_WINDOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATTN_SMEM));
+      KDB_CUDA(cudaFuncSetAttribute(attn_tc_kernel<MODE_WINDOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATTN_SMEM_WINDOW));
       attr_w = true;
     }
     p.nblk = 1;
     dim3 grid((unsigned)((h / 8) * (w / 8)), (unsigned)(nh / 2), (unsigned)B);
-    attn_tc_kernel<MODE_WINDOW><<<grid, 160, ATTN_SMEM, st>>>(tm, p);
+    attn_tc_kernel<MODE_WINDOW><<<grid, 160, ATTN_SMEM_WINDOW, st>>>(tm, p);
   } else {
     const uint64_t T = (uint64_t)h * w;
     const uint64_t dims[3] = {F, T, (uint64_t)B};
