@@ -10,6 +10,10 @@
 //            is fetched as four 4x4-token TMA boxes (quadrants), which are exactly the seam-mask regions (:300-315).
 //   GLOBAL : rows = 128 queries of one head; keys streamed in blocks of 128; exact two-pass softmax
 //            (pass A: row maxima, pass B: exp / P V) so no accumulator rescaling is needed.
+//   NA     : 7x7 neighbourhood attention (reference :399-443 via natten; NATTEN definition: window clamped inward at the
+//            borders, always 49 keys).  Rows = an 8x16 query block of one head; its keys all lie in the clamped 14x22 halo,
+//            streamed as three TMA boxes of 5 halo rows (110 keys per 128-row tile, the tail rows are masked / zero);
+//            the per-query 7x7 window is a mask on S.  Same two-pass softmax as GLOBAL.
 // Pipeline per key block: TMA (SWIZZLE_128B) -> S = Q K^T (tcgen05.mma, fp32 in TMEM) -> tcgen05.ld, softmax in
 // registers (one thread per row) -> P (bf16) written to shared memory in the UMMA K-major SW128 layout ->
 // O += P V (V consumed as an MN-major operand straight from the TMA tile) -> tcgen05.ld, 1/l scaling, store.
@@ -23,7 +27,12 @@ constexpr int ROWS = 128, DH = 64;
 constexpr int TILE_BYTES = ROWS * DH * 2;    // 16 KiB: 128 rows x 128 B
 constexpr float LOG2E = 1.4426950408889634f;
 
-enum { MODE_WINDOW = 0, MODE_GLOBAL = 1 };
+enum { MODE_WINDOW = 0, MODE_GLOBAL = 1, MODE_NA = 2 };
+
+constexpr int NA_QH = 8, NA_QW = 16;          // query block of one CTA (128 queries of one head)
+constexpr int NA_KH = 14, NA_KW = 22;         // its clamped key halo for a 7x7 neighbourhood
+constexpr int NA_BLK_ROWS = 5;                // halo rows per key block: 5 x 22 = 110 keys (of a 128-row tile)
+constexpr int NA_BLK_KEYS = NA_BLK_ROWS * NA_KW;
 
 struct AttnParams {
   bf16* out;
@@ -40,7 +49,8 @@ __device__ __forceinline__ uint32_t p_offset(int row, int chunk16) {   // byte o
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(160, MODE == MODE_WINDOW ? 4 : 2) attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, const AttnParams p) {
+__global__ void __launch_bounds__(160, MODE == MODE_WINDOW ? 4 : 2) attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_kv,
+                                                                                      const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = base;
@@ -64,6 +74,14 @@ __global__ void __launch_bounds__(160, MODE == MODE_WINDOW ? 4 : 2) attn_tc_kern
     mtile = blockIdx.x;
     head0 = blockIdx.y;
   }
+  int qi0 = 0, qj0 = 0, r0 = 0, c0 = 0;      // NA: query block origin and clamped halo origin
+  if constexpr (MODE == MODE_NA) {
+    const int nbw = p.w / NA_QW;
+    qi0 = (blockIdx.x / nbw) * NA_QH;
+    qj0 = (blockIdx.x % nbw) * NA_QW;
+    r0 = min(max(qi0 - 3, 0), p.h - NA_KH);
+    c0 = min(max(qj0 - 3, 0), p.w - NA_KW);
+  }
   const int nblk = (MODE == MODE_WINDOW) ? 1 : p.nblk;
   const bool two_pass = nblk > 1;
 
@@ -76,6 +94,11 @@ __global__ void __launch_bounds__(160, MODE == MODE_WINDOW ? 4 : 2) attn_tc_kern
     tc::mbar_init(&bars->p, 128);
     tc::mbar_init(&bars->o, 1);
     tc::fence_barrier_init();
+  }
+  if constexpr (MODE == MODE_NA) {   // rows 110..127 of the V tile are never written by TMA: they must be finite (P there is exactly 0)
+    for (int i = threadIdx.x; i < (ROWS - NA_BLK_KEYS) * 8; i += blockDim.x)
+      *reinterpret_cast<uint4*>(sV + NA_BLK_KEYS * 128 + i * 16) = make_uint4(0u, 0u, 0u, 0u);
+    tc::fence_proxy_async();
   }
   constexpr uint32_t TMEM_COLS = (MODE == MODE_WINDOW) ? 128 : 256;
   if (warp == 4) tc::tmem_alloc(&bars->tmem, TMEM_COLS);
@@ -107,6 +130,8 @@ __global__ void __launch_bounds__(160, MODE == MODE_WINDOW ? 4 : 2) attn_tc_kern
       tc::mbar_arrive_expect_tx(&bars->q, TILE_BYTES);
       if constexpr (MODE == MODE_WINDOW)
         load_window_tile(sQ, 0, &bars->q);
+      else if constexpr (MODE == MODE_NA)
+        tc::tma_load_4d(sQ, &tmap, &bars->q, head0 * DH, qj0, qi0, b);
       else
         tc::tma_load_3d(sQ, &tmap, &bars->q, head0 * DH, mtile * ROWS, b);
 
@@ -122,10 +147,14 @@ __global__ void __launch_bounds__(160, MODE == MODE_WINDOW ? 4 : 2) attn_tc_kern
       for (int pass = two_pass ? 0 : 1; pass < 2; ++pass) {
         for (int j = 0; j < nblk; ++j, ++it) {
           const bool with_v = pass == 1;
-          tc::mbar_arrive_expect_tx(&bars->kv, with_v ? 2 * TILE_BYTES : TILE_BYTES);
+          constexpr uint32_t KV_BYTES = (MODE == MODE_NA) ? NA_BLK_KEYS * 128 : TILE_BYTES;
+          tc::mbar_arrive_expect_tx(&bars->kv, with_v ? 2 * KV_BYTES : KV_BYTES);
           if constexpr (MODE == MODE_WINDOW) {
             load_window_tile(sK, 1, &bars->kv);
             load_window_tile(sV, 2, &bars->kv);
+          } else if constexpr (MODE == MODE_NA) {
+            tc::tma_load_4d(sK, &tmap_kv, &bars->kv, (nh + head0) * DH, c0, r0 + j * NA_BLK_ROWS, b);
+            if (with_v) tc::tma_load_4d(sV, &tmap_kv, &bars->kv, (2 * nh + head0) * DH, c0, r0 + j * NA_BLK_ROWS, b);
           } else {
             tc::tma_load_3d(sK, &tmap, &bars->kv, (nh + head0) * DH, j * ROWS, b);
             if (with_v) tc::tma_load_3d(sV, &tmap, &bars->kv, (2 * nh + head0) * DH, j * ROWS, b);
@@ -171,6 +200,15 @@ __global__ void __launch_bounds__(160, MODE == MODE_WINDOW ? 4 : 2) attn_tc_kern
     const int hd = row >> 6, quad = (row & 63) >> 4;
     const bool seam_r = MODE == MODE_WINDOW && p.shift > 0 && wi == 0;
     const bool seam_c = MODE == MODE_WINDOW && p.shift > 0 && wj == 0;
+    // NA: this row's query and the origin of its clamped 7x7 window
+    const int na_qi = qi0 + (row >> 4), na_qj = qj0 + (row & 15);
+    const int na_rs = min(max(na_qi - 3, 0), p.h - 7), na_cs = min(max(na_qj - 3, 0), p.w - 7);
+    auto key_ok = [&](int j, int t) -> bool {      // is tile column t of key block j inside this row's neighbourhood?
+      if constexpr (MODE != MODE_NA) return true;
+      const int dr = (t * 745) >> 14;               // t / 22 for t < 128
+      const int kr = r0 + j * NA_BLK_ROWS + dr, kc = c0 + (t - dr * NA_KW);
+      return t < NA_BLK_KEYS && (unsigned)(kr - na_rs) < 7u && (unsigned)(kc - na_cs) < 7u;
+    };
     for (int pass = two_pass ? 0 : 1; pass < 2; ++pass) {
       for (int j = 0; j < nblk; ++j, ++it) {
         tc::mbar_wait(&bars->s, it & 1u);
@@ -181,11 +219,11 @@ __global__ void __launch_bounds__(160, MODE == MODE_WINDOW ? 4 : 2) attn_tc_kern
             float v[32];
             tc::tmem_ld32(tmem_s + lane_base + c * 32, v);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) m = fmaxf(m, v[i]);
+            for (int i = 0; i < 32; ++i) m = fmaxf(m, key_ok(j, c * 32 + i) ? v[i] : -INFINITY);
           }
           tc::tc_fence_before();
           tc::mbar_arrive(&bars->sc);
-        } else if constexpr (MODE == MODE_GLOBAL) {
+        } else if constexpr (MODE != MODE_WINDOW) {
           const float mb = m * LOG2E;
 #pragma unroll 1
           for (int c = 0; c < 4; ++c) {
@@ -206,7 +244,8 @@ __global__ void __launch_bounds__(160, MODE == MODE_WINDOW ? 4 : 2) attn_tc_kern
             uint32_t pk[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const float p0 = exp2f(fmaf(v[2 * i], LOG2E, -mbb)), p1 = exp2f(fmaf(v[2 * i + 1], LOG2E, -mbb));
+              const float p0 = key_ok(j, c * 32 + 2 * i) ? exp2f(fmaf(v[2 * i], LOG2E, -mbb)) : 0.f;
+              const float p1 = key_ok(j, c * 32 + 2 * i + 1) ? exp2f(fmaf(v[2 * i + 1], LOG2E, -mbb)) : 0.f;
               pk[i] = tc::pack_bf16x2(p0, p1);
               float q0, q1;
               tc::unpack_bf16x2(pk[i], q0, q1);     // l accumulates exactly what the P V MMA sees
@@ -278,6 +317,9 @@ __global__ void __launch_bounds__(160, MODE == MODE_WINDOW ? 4 : 2) attn_tc_kern
       }
       token = (int64_t)oi * p.w + oj;
       head = head0 + hd;
+    } else if constexpr (MODE == MODE_NA) {
+      token = (int64_t)na_qi * p.w + na_qj;
+      head = head0;
     } else {
       token = (int64_t)mtile * ROWS + row;
       head = head0;
@@ -316,6 +358,7 @@ bool tc_attention_supported(int h, int w, int nh, int e, int attn_type, int attn
   if (g_attn_tc_disabled || e != 64) return false;
   if (attn_type == KDB_ATTN_SHIFTED_WINDOW) return attn_param == 8 && h % 8 == 0 && w % 8 == 0 && nh % 2 == 0;
   if (attn_type == KDB_ATTN_GLOBAL) return (h * w) % 128 == 0 && (h * w) / 128 <= 64;
+  if (attn_type == KDB_ATTN_NEIGHBORHOOD) return attn_param == 7 && h % NA_QH == 0 && w % NA_QW == 0 && h >= NA_KH && w >= NA_KW;
   return false;
 }
 
@@ -343,7 +386,23 @@ int launch_attention_tc(const bf16* qkv, bf16* out, int B, int h, int w, int nh,
     }
     p.nblk = 1;
     dim3 grid((unsigned)((h / 8) * (w / 8)), (unsigned)(nh / 2), (unsigned)B);
-    attn_tc_kernel<MODE_WINDOW><<<grid, 160, ATTN_SMEM_WINDOW, st>>>(tm, p);
+    attn_tc_kernel<MODE_WINDOW><<<grid, 160, ATTN_SMEM_WINDOW, st>>>(tm, tm, p);
+  } else if (attn_type == KDB_ATTN_NEIGHBORHOOD) {
+    static bool attr_n = false;
+    CUtensorMap tkv;
+    const uint64_t dims[4] = {F, (uint64_t)w, (uint64_t)h, (uint64_t)B};
+    const uint64_t strides[3] = {F * 2, F * 2 * w, F * 2 * w * h};
+    const uint32_t box_q[4] = {DH, NA_QW, NA_QH, 1}, box_kv[4] = {DH, NA_KW, NA_BLK_ROWS, 1};
+    int rc = make_tmap_bf16(&tm, qkv, 4, dims, strides, box_q);
+    if (rc) return rc;
+    if ((rc = make_tmap_bf16(&tkv, qkv, 4, dims, strides, box_kv))) return rc;
+    if (!attr_n) {
+      KDB_CUDA(cudaFuncSetAttribute(attn_tc_kernel<MODE_NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATTN_SMEM));
+      attr_n = true;
+    }
+    p.nblk = 3;      // 14 halo rows = 5 + 5 + 4
+    dim3 grid((unsigned)((h / NA_QH) * (w / NA_QW)), (unsigned)nh, (unsigned)B);
+    attn_tc_kernel<MODE_NA><<<grid, 160, ATTN_SMEM, st>>>(tm, tkv, p);
   } else {
     const uint64_t T = (uint64_t)h * w;
     const uint64_t dims[3] = {F, T, (uint64_t)B};
@@ -357,7 +416,7 @@ int launch_attention_tc(const bf16* qkv, bf16* out, int B, int h, int w, int nh,
     }
     p.nblk = (int)(T / ROWS);
     dim3 grid((unsigned)(T / ROWS), (unsigned)nh, (unsigned)B);
-    attn_tc_kernel<MODE_GLOBAL><<<grid, 160, ATTN_SMEM, st>>>(tm, p);
+    attn_tc_kernel<MODE_GLOBAL><<<grid, 160, ATTN_SMEM, st>>>(tm, tm, p);
   }
   KDB_LAUNCH_CHECK(F_ATTN_TC, st);
   return 0;

@@ -137,6 +137,31 @@ def test_neighborhood_model_vs_oracle():
     assert_close(model(x.to(DEV), sig.to(DEV)), O.make_denoiser(sd, cfg["model"])(x, sig), what="NA denoised")
 
 
+def test_neighborhood_model_bf16_tensor_core_path():
+    """128x128 input -> 32x32 tokens at level 0: the tcgen05 neighbourhood kernel (level 1 = 16x16 stays on the generic one)."""
+    raw = {"model": dict(NA_CFG["model"], input_size=[128, 128], depths=[1, 1, 1])}
+    cfg, sd, inner, model, _ = build(raw, precision="bf16")
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(2, 3, 128, 128, generator=g) * 10
+    sig = torch.tensor([0.9, 12.0])
+    want = O.make_denoiser(sd, cfg["model"])(x, sig)
+    assert rel_l2(model(x.to(DEV), sig.to(DEV)), want) < 2e-2
+
+
+def test_cfg5_shape_512_forward_b1():
+    """BASELINE configs[4] model (512x512, widths 256/512/1024, depths 2/2/4, NA,NA,global) at B=1: bf16 path vs the fp32 oracle.
+    Exercises the 1024-token global attention (8 key blocks, two-pass) and the NA kernel on 128x128 / 64x64 token grids."""
+    raw = {"model": {"type": "image_transformer_v2", "input_channels": 3, "input_size": [512, 512], "patch_size": [4, 4],
+                     "depths": [2, 2, 4], "widths": [256, 512, 1024], "sigma_data": 0.5, "sigma_min": 1e-2, "sigma_max": 160}}
+    cfg, sd, inner, model, _ = build(raw, precision="bf16")
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(1, 3, 512, 512, generator=g) * 5
+    sig = torch.tensor([2.0])
+    want = O.make_denoiser(sd, cfg["model"])(x, sig)
+    got = model(x.to(DEV), sig.to(DEV))
+    assert torch.isfinite(got).all() and rel_l2(got, want) < 2e-2
+
+
 def test_nonsquare_and_mapping_cond():
     raw = {"model": {"type": "image_transformer_v2", "input_channels": 2, "input_size": [32, 64], "patch_size": [2, 4],
                      "depths": [1, 2], "widths": [64, 128], "mapping_cond_dim": 5, "sigma_data": 1.0,

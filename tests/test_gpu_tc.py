@@ -59,7 +59,9 @@ def _ref_attention(qkv, h, w, nh, kind, param, shift):
 @pytest.mark.parametrize("B,h,w,nh,kind,param,shift", [
     (2, 16, 16, 2, "shifted-window", 8, 0), (2, 16, 16, 2, "shifted-window", 8, 4), (1, 8, 8, 4, "shifted-window", 8, 4),
     (3, 64, 64, 2, "shifted-window", 8, 4), (2, 32, 24, 4, "shifted-window", 8, 0),
-    (2, 16, 16, 8, "global", 0, 0), (1, 8, 16, 2, "global", 0, 0), (1, 32, 32, 4, "global", 0, 0), (2, 16, 24, 1, "global", 0, 0)])
+    (2, 16, 16, 8, "global", 0, 0), (1, 8, 16, 2, "global", 0, 0), (1, 32, 32, 4, "global", 0, 0), (2, 16, 24, 1, "global", 0, 0),
+    (2, 16, 32, 2, "neighborhood", 7, 0), (1, 64, 64, 2, "neighborhood", 7, 0), (2, 32, 32, 4, "neighborhood", 7, 0),
+    (1, 24, 48, 1, "neighborhood", 7, 0), (1, 16, 112, 3, "neighborhood", 7, 0)])
 def test_attention_tcgen05_vs_reference(B, h, w, nh, kind, param, shift):
     from k_diffusion import _native as N_
     qkv = _qkv(B, h, w, nh, seed=h * w + nh + shift)
