@@ -51,6 +51,7 @@ struct KdbModel {
   std::vector<bf16*> merge_wb, split_wb;
   std::vector<void*> owned;
   float* ada_cat = nullptr;
+  bf16* patch_out_wb = nullptr;     // patch_out.proj.weight zero-padded to 64 rows (tensor-core patch-out)
   int ada_total = 0;
   CondWeights cw{};
   std::map<std::pair<int, int>, PosTables> pos_cache;
@@ -449,6 +450,14 @@ int forward_impl(KdbModel* m, int B, int H, int W, const float* x, const float* 
     if ((rc = tap<T>(m, "L" + std::to_string(l) + ".up", up, (int64_t)B * h * w * c.width[l], st))) return rc;
     cur = up;
   }
+  if (std::is_same<T, bf16>::value && m->patch_out_wb != nullptr &&
+      tc_patch_out_supported(c.width[0], c.out_channels, c.patch_h, c.patch_w, W)) {
+    // out_norm as a row kernel, then the projection on the tensor core with un-patch + Karras combine in its epilogue
+    T* xn = reinterpret_cast<T*>(ws.xn);
+    const int64_t M0 = (int64_t)B * h0 * w0;
+    if ((rc = launch_rmsnorm<T>(cur, xn, out_norm, 0, M0, M0, c.width[0], st))) return rc;
+    return launch_patch_out_tc(reinterpret_cast<const bf16*>(xn), m->patch_out_wb, x, sigma, sd, out, B, H, W, c.width[0], st);
+  }
   return launch_patch_out<T>(cur, out_norm, patch_out_w, x, sigma, sd, out, B, c.out_channels, H, W, c.patch_h, c.patch_w, c.width[0], st);
 }
 
@@ -542,6 +551,15 @@ int kdb_model_finalize(KdbModel* m, void* stream) {
   GET("out_norm.scale", &tmp, c.width[0]);
   GET("patch_out.proj.weight", &tmp, (int64_t)c.patch_h * c.patch_w * c.out_channels, c.width[0]);
 
+  {   // zero-padded bf16 patch_out weight [64, C0]
+    const int Np = c.patch_h * c.patch_w * c.out_channels, C0 = c.width[0];
+    m->patch_out_wb = nullptr;
+    if (Np <= 64) {
+      if ((rc = dev_alloc(m, &m->patch_out_wb, (size_t)64 * C0))) return rc;
+      KDB_CUDA(cudaMemsetAsync(m->patch_out_wb, 0, (size_t)64 * C0 * sizeof(bf16), st));
+      if ((rc = launch_f32_to_bf16(tmp, m->patch_out_wb, (int64_t)Np * C0, st))) return rc;
+    }
+  }
   // conditioning weights
   CondWeights& w = m->cw;
   w = CondWeights{};

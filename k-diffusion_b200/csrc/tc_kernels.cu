@@ -63,7 +63,7 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KiB
 constexpr int SUB_TILE_BYTES = BM * 128;     // one [128 x 64] bf16 output sub-tile
 constexpr int MAX_STAGES = 4;
 
-enum TcEpi { TCE_STORE = 0, TCE_RESID = 1, TCE_GEGLU = 2, TCE_SPLIT = 3, TCE_QKV = 4 };
+enum TcEpi { TCE_STORE = 0, TCE_RESID = 1, TCE_GEGLU = 2, TCE_SPLIT = 3, TCE_QKV = 4, TCE_PATCHOUT = 5 };
 
 struct TcParams {
   bf16* out;
@@ -76,6 +76,12 @@ struct TcParams {
   const float2* rope;    // [T, nh, 16]
   const float* qk_scale; // [nh]
   int C, nh, T;
+  // PATCHOUT (4x4 patches, 3 output channels): un-patch to NCHW fp32 + Karras combine with the input latent
+  float* fout;
+  const float* x_in;
+  const float* sigma;
+  float sd;
+  int H, Wimg, th, tw;
   int a_merge, mwc, mC;  // A operand gathered from fine tokens (TokenMerge): coarse grid width, fine channels
   int box_w, box_h;      // 5-D TMA boxes of merge / split: 128 rows = box_h x box_w coarse tokens
   long long* trace;      // debug: per-tile clock64 stamps of CTA 0 (KDB200_GEMM_TRACE=1), else nullptr
@@ -152,7 +158,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   if (threadIdx.x == 0) {
     tc::tma_prefetch_desc(&tma);
     tc::tma_prefetch_desc(&tmb);
-    if constexpr (EPI != TCE_SPLIT) tc::tma_prefetch_desc(&tmc);
+    if constexpr (EPI != TCE_SPLIT && EPI != TCE_PATCHOUT) tc::tma_prefetch_desc(&tmc);
     for (int s = 0; s < p.stages; ++s) {
       tc::mbar_init(&full[s], 1);
       tc::mbar_init(&empty[s], 1);
@@ -209,7 +215,40 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
     const int row = q * 32 + lane;
     const int64_t m = m0 + row;
     const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
-    if constexpr (EPI == TCE_SPLIT) {
+    if constexpr (EPI == TCE_PATCHOUT) {
+      // TokenSplitWithoutSkip 4x4 + NCHW + Denoiser combine (reference :598-607,:758-760, layers.py:88-90).  Row m = token
+      // (b, ty, tx); column n = (nh*4 + nw)*3 + c.  For fixed (c, nh) the 4 nw pixels are one float4, and consecutive lanes are
+      // consecutive tokens of a row -> every warp-wide load / store is 512 contiguous bytes.
+      float v[64];
+      {
+        float t0[32], t1[32];
+        tc::tmem_ld32(taddr, t0);
+        tc::tmem_ld32(taddr + 32, t1);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { v[i] = t0[i]; v[32 + i] = t1[i]; }
+      }
+      if (m < p.M) {
+        const int per = p.th * p.tw;
+        const int b = (int)(m / per);
+        const int r = (int)(m - (int64_t)b * per);
+        const int ty = r / p.tw, tx = r - ty * p.tw;
+        float c_skip = 0.f, c_out = 1.f, c_in;
+        if (p.sd > 0.f) karras_scalings(__ldg(p.sigma + b), p.sd, c_skip, c_out, c_in);
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int nh = 0; nh < 4; ++nh) {
+            const int64_t o = (((int64_t)b * 3 + c) * p.H + (ty * 4 + nh)) * p.Wimg + tx * 4;
+            float4 y = make_float4(bf16_round(v[(nh * 4 + 0) * 3 + c]), bf16_round(v[(nh * 4 + 1) * 3 + c]), bf16_round(v[(nh * 4 + 2) * 3 + c]),
+                                   bf16_round(v[(nh * 4 + 3) * 3 + c]));
+            if (p.sd > 0.f) {
+              const float4 xi = __ldg(reinterpret_cast<const float4*>(p.x_in + o));
+              y = make_float4(y.x * c_out + xi.x * c_skip, y.y * c_out + xi.y * c_skip, y.z * c_out + xi.z * c_skip, y.w * c_out + xi.w * c_skip);
+            }
+            *reinterpret_cast<float4*>(p.fout + o) = y;
+          }
+      }
+    } else if constexpr (EPI == TCE_SPLIT) {
       // TokenSplit: row m = (b, hy, wx) on the coarse grid; 32 columns inside one (nh, nw) quadrant (Cf % 32 == 0)
       const bool live = m < p.M;
       const float facv = __ldg(p.fac);
@@ -356,7 +395,7 @@ int launch_tc(const bf16* A, const bf16* W, const TcParams& p, cudaStream_t st) 
   if ((rc = tmap_2d(&ta, A, (uint64_t)p.K, (uint64_t)p.M, BK, BM))) return rc;
   if ((rc = tmap_2d(&tb, W, (uint64_t)p.K, (uint64_t)p.N, BK, BN))) return rc;
   const uint64_t n_out = EPI == TCE_GEGLU ? (uint64_t)p.N / 2 : (uint64_t)p.N;
-  if (EPI != TCE_SPLIT) {
+  if (EPI != TCE_SPLIT && EPI != TCE_PATCHOUT) {
     if ((rc = tmap_2d(&tcm, p.out, n_out, (uint64_t)p.M, 64, BM))) return rc;
   } else {
     tcm = ta;
@@ -461,6 +500,30 @@ int launch_gemm_tc(const bf16* A, const bf16* W, bf16* C, int64_t M, int N, int 
     default:
       KDB_REQUIRE(false, KDB_ERR_BAD_ARG, "gemm_tc: bad epilogue");
   }
+}
+
+// patch_out on the tensor core: tokens already normalised (xn bf16 [M, C0]), W zero-padded to [64, C0]
+bool tc_patch_out_supported(int C0, int Cout, int ph, int pw, int Wimg) {
+  return !g_tc_disabled && C0 % 64 == 0 && Cout == 3 && ph == 4 && pw == 4 && Wimg % 4 == 0;
+}
+
+int launch_patch_out_tc(const bf16* xn, const bf16* W_pad, const float* x_in, const float* sigma, float sigma_data, float* out, int B, int H,
+                        int Wimg, int C0, cudaStream_t st) {
+  TcParams p{};
+  p.M = (int64_t)B * (H / 4) * (Wimg / 4);
+  p.N = 64;
+  p.K = C0;
+  p.stages = pick_stages(C0, false);
+  p.fout = out;
+  p.x_in = x_in;
+  p.sigma = sigma;
+  p.sd = sigma_data;
+  p.H = H;
+  p.Wimg = Wimg;
+  p.th = H / 4;
+  p.tw = Wimg / 4;
+  KDB_REQUIRE(shape_ok(p.M, 64, C0), KDB_ERR_BAD_SHAPE, "patch_out_tc: unsupported shape");
+  return launch_tc<64, TCE_PATCHOUT>(xn, W_pad, p, st);
 }
 
 bool tc_gemm_geglu_supported(int64_t M, int N2, int K) { return !g_tc_disabled && shape_ok(M, N2, K) && N2 % 128 == 0; }

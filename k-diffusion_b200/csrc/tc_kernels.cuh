@@ -12,6 +12,11 @@ int launch_gemm_tc(const bf16* A, const bf16* W, bf16* C, int64_t M, int N, int 
 bool tc_gemm_geglu_supported(int64_t M, int N2, int K);
 int launch_gemm_tc_geglu(const bf16* A, const bf16* W_il, bf16* out, int64_t M, int N2, int K, cudaStream_t st);
 
+// patch_out (4x4 patches, 3 channels): xn bf16 [M, C0] x W_pad bf16 [64, C0] -> fp32 NCHW with the Karras combine fused
+bool tc_patch_out_supported(int C0, int Cout, int ph, int pw, int Wimg);
+int launch_patch_out_tc(const bf16* xn, const bf16* W_pad, const float* x_in, const float* sigma, float sigma_data, float* out, int B, int H,
+                        int Wimg, int C0, cudaStream_t st);
+
 bool tc_attention_supported(int h, int w, int nh, int e, int attn_type, int attn_param);
 int launch_attention_tc(const bf16* qkv, bf16* out, int B, int h, int w, int nh, int e, int attn_type, int attn_param, int shift,
                         cudaStream_t st);

@@ -53,8 +53,10 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--json", default=None)
+    ap.add_argument("--config", default="sw", choices=["sw", "na"], help="sw = cfg2 shifted-window model, na = cfg3/4 neighbourhood model")
     args = ap.parse_args()
-    cfg = K.config.load_config(json.loads((ROOT / "tests/golden/cfg2_sw256_shapes.json").read_text())["config"])
+    fixture = "cfg2_sw256_shapes.json" if args.config == "sw" else "cfg3_na256_config.json"
+    cfg = K.config.load_config(json.loads((ROOT / "tests/golden" / fixture).read_text())["config"])
     inner = K.synth.synth_init_(K.config.make_model(cfg), seed=1).cuda().eval().set_precision(args.precision)
     model = K.Denoiser(inner, sigma_data=cfg["model"]["sigma_data"])
     x = torch.randn(args.batch, 3, 256, 256, device="cuda") * 10
