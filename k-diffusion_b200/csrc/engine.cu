@@ -30,6 +30,7 @@ struct LayerPlan {
   bf16 *qkv_wb = nullptr, *out_wb = nullptr, *up_wb = nullptr, *down_wb = nullptr;
   bf16* up_wb_il = nullptr;          // up_proj rows interleaved (value/gate) for the fused GEGLU epilogue
   int exec_index = 0;                // position in execution order (indexes PosTables::rope)
+  bf16 *qkv_wf = nullptr, *up_wf = nullptr;   // per-evaluation copies with the AdaRMSNorm channel scale folded in (fused norm)
 };
 
 struct PosTables {
@@ -51,7 +52,12 @@ struct KdbModel {
   std::vector<bf16*> merge_wb, split_wb;
   std::vector<void*> owned;
   float* ada_cat = nullptr;
+  FoldDesc* fold_descs = nullptr;   // device table for launch_fold_norm_weights
+  int n_fold = 0;
+  bool fuse_norm = true;
+  bool ss_valid = false;            // ws.rowss describes the current residual stream (set by the GEMM that produced it)
   bf16* patch_out_wb = nullptr;     // patch_out.proj.weight zero-padded to 64 rows (tensor-core patch-out)
+  bf16* patch_out_wf = nullptr;     // the same with out_norm.scale folded in (fused out_norm)
   int ada_total = 0;
   CondWeights cw{};
   std::map<std::pair<int, int>, PosTables> pos_cache;
@@ -150,6 +156,7 @@ int plan_layer(KdbModel* m, LayerPlan& L, const std::string& prefix, int level, 
     int rc;
     if ((rc = make_bf16(m, L.qkv_w, 3LL * L.C * L.C, &L.qkv_wb, st))) return rc;
     if ((rc = make_bf16(m, L.out_w, (int64_t)L.C * L.C, &L.out_wb, st))) return rc;
+    if ((rc = dev_alloc(m, &L.qkv_wf, (size_t)3 * L.C * L.C))) return rc;
   }
   const std::string f = prefix + "ff.";
   GET(f + "norm.linear.weight", &L.ff_norm_w, L.C, mw);
@@ -164,6 +171,7 @@ int plan_layer(KdbModel* m, LayerPlan& L, const std::string& prefix, int level, 
     if ((rc = dev_alloc(m, &L.up_wb_il, (size_t)2 * L.dff * L.C))) return rc;
     interleave_geglu_rows_kernel<<<kNumSMs * 4, 256, 0, st>>>(L.up_w, L.up_wb_il, L.dff, L.C);
     KDB_LAUNCH_CHECK(F_CONVERT, st);
+    if ((rc = dev_alloc(m, &L.up_wf, (size_t)2 * L.dff * L.C))) return rc;
   }
   return 0;
 }
@@ -246,6 +254,7 @@ int ensure_pos(KdbModel* m, int h0, int w0, cudaStream_t st, PosTables** out) {
 struct Workspace {
   std::vector<char*> xs, xup;
   char *xn = nullptr, *qkv = nullptr, *ao = nullptr, *hbuf = nullptr, *gbuf = nullptr, *mg = nullptr;
+  float* rowss = nullptr;   // [tokens at level 0, SS_PARTS] sum(x^2) of the current residual stream (fused RMSNorm)
   size_t total = 0;
 };
 
@@ -278,6 +287,7 @@ void carve(const KdbModelConfig& c, int prec, int B, int H, int W, char* base, W
   ws.hbuf = take(mh);
   ws.gbuf = take(mh / 2);
   ws.mg = take(mg);
+  ws.rowss = reinterpret_cast<float*>(take((size_t)B * (H / c.patch_h) * (W / c.patch_w) * SS_PARTS * sizeof(float)));
   ws.total = off + 1024;
 }
 
@@ -338,22 +348,33 @@ int run_layer(KdbModel* m, const LayerPlan& L, T* x, int B, int h, int w, const 
   T* gb = reinterpret_cast<T*>(ws.gbuf);
   const std::string tag = "layer" + std::to_string(m->layer_counter++);
   int rc;
+  // fused RMSNorm: possible when the whole batch shares one conditioning row (folded weights are per evaluation) and the GEMM
+  // that produced x left its row statistics in ws.rowss
+  const bool emit = std::is_same<T, bf16>::value && m->fuse_norm && C % 128 == 0;
+  const bool fold = emit && cond_bs == 0 && m->fold_descs != nullptr;
   if (L.attn_type != KDB_ATTN_NONE) {
-    if ((rc = launch_rmsnorm<T>(x, xn, cond + L.ada_attn, cond_bs, Ttok, M, C, st))) return rc;
-    if ((rc = tap<T>(m, tag + ".xn1", xn, M * C, st))) return rc;
     GemmEpi qe;
-    qe.mode = EPI_QKV_ROPE;
+    qe.mode = (L.e == 64 && pt->rope[L.exec_index] != nullptr) ? EPI_QKV_ROPE : EPI_STORE;
     qe.C = C;
     qe.nh = L.nh;
     qe.T_tokens = (int)Ttok;
     qe.rope = pt->rope[L.exec_index];
     qe.qk_scale = L.scale;
-    if (std::is_same<T, bf16>::value && L.e == 64 && tc_gemm_supported(M, 3 * C, C, qe)) {
-      // cosine-sim scaling + RoPE fused into the qkv projection's epilogue
-      if ((rc = launch_gemm_tc(reinterpret_cast<const bf16*>(xn), L.qkv_wb, reinterpret_cast<bf16*>(qkv), M, 3 * C, C, qe, st))) return rc;
+    GemmEpi qf = qe;
+    qf.ss_in = ws.rowss;
+    if (fold && m->ss_valid && L.qkv_wf != nullptr && tc_gemm_supported(M, 3 * C, C, qf)) {
+      if ((rc = launch_gemm_tc(reinterpret_cast<const bf16*>(x), L.qkv_wf, reinterpret_cast<bf16*>(qkv), M, 3 * C, C, qf, st))) return rc;
+      if (qf.mode == EPI_STORE && (rc = launch_qknorm_rope<T>(qkv, pos, L.freqs, L.scale, M, (int)Ttok, L.nh, L.e, st))) return rc;
     } else {
-      if ((rc = linear<T>(xn, WSel<T>::qkv(L), qkv, M, 3 * C, C, GemmEpi{}, st))) return rc;
-      if ((rc = launch_qknorm_rope<T>(qkv, pos, L.freqs, L.scale, M, (int)Ttok, L.nh, L.e, st))) return rc;
+      if ((rc = launch_rmsnorm<T>(x, xn, cond + L.ada_attn, cond_bs, Ttok, M, C, st))) return rc;
+      if ((rc = tap<T>(m, tag + ".xn1", xn, M * C, st))) return rc;
+      if (std::is_same<T, bf16>::value && qe.mode == EPI_QKV_ROPE && tc_gemm_supported(M, 3 * C, C, qe)) {
+        // cosine-sim scaling + RoPE fused into the qkv projection's epilogue
+        if ((rc = launch_gemm_tc(reinterpret_cast<const bf16*>(xn), L.qkv_wb, reinterpret_cast<bf16*>(qkv), M, 3 * C, C, qe, st))) return rc;
+      } else {
+        if ((rc = linear<T>(xn, WSel<T>::qkv(L), qkv, M, 3 * C, C, GemmEpi{}, st))) return rc;
+        if ((rc = launch_qknorm_rope<T>(qkv, pos, L.freqs, L.scale, M, (int)Ttok, L.nh, L.e, st))) return rc;
+      }
     }
     if ((rc = tap<T>(m, tag + ".qkv", qkv, M * 3 * C, st))) return rc;
     if ((rc = attention_dispatch<T>(qkv, ao, B, h, w, L.nh, L.e, L.attn_type, L.attn_param, L.shift, st))) return rc;
@@ -361,12 +382,19 @@ int run_layer(KdbModel* m, const LayerPlan& L, T* x, int B, int h, int w, const 
     GemmEpi e;
     e.mode = EPI_RESID;
     e.resid = x;
+    m->ss_valid = emit && tc_gemm_emits_rowss(M, C, C, e);
+    if (m->ss_valid) e.ss_out = ws.rowss;
     if ((rc = linear<T>(ao, WSel<T>::out(L), x, M, C, C, e, st))) return rc;
     if ((rc = tap<T>(m, tag + ".attn", x, M * C, st))) return rc;
   }
-  if ((rc = launch_rmsnorm<T>(x, xn, cond + L.ada_ff, cond_bs, Ttok, M, C, st))) return rc;
   bool fused_geglu = false;
-  if (std::is_same<T, bf16>::value && L.up_wb_il != nullptr && tc_gemm_geglu_supported(M, 2 * L.dff, C)) {
+  if (fold && m->ss_valid && L.up_wf != nullptr && tc_gemm_geglu_supported(M, 2 * L.dff, C, true)) {
+    if ((rc = launch_gemm_tc_geglu(reinterpret_cast<const bf16*>(x), L.up_wf, reinterpret_cast<bf16*>(gb), M, 2 * L.dff, C, st, ws.rowss))) return rc;
+    fused_geglu = true;
+  } else if ((rc = launch_rmsnorm<T>(x, xn, cond + L.ada_ff, cond_bs, Ttok, M, C, st))) {
+    return rc;
+  }
+  if (!fused_geglu && std::is_same<T, bf16>::value && L.up_wb_il != nullptr && tc_gemm_geglu_supported(M, 2 * L.dff, C)) {
     if ((rc = launch_gemm_tc_geglu(reinterpret_cast<const bf16*>(xn), L.up_wb_il, reinterpret_cast<bf16*>(gb), M, 2 * L.dff, C, st)))
       return rc;
     fused_geglu = true;
@@ -379,6 +407,8 @@ int run_layer(KdbModel* m, const LayerPlan& L, T* x, int B, int h, int w, const 
   GemmEpi e;
   e.mode = EPI_RESID;
   e.resid = x;
+  m->ss_valid = emit && tc_gemm_emits_rowss(M, C, L.dff, e);
+  if (m->ss_valid) e.ss_out = ws.rowss;
   if ((rc = linear<T>(gb, WSel<T>::down(L), x, M, C, L.dff, e, st))) return rc;
   return tap<T>(m, tag + ".ff", x, M * C, st);
 }
@@ -400,6 +430,9 @@ int forward_impl(KdbModel* m, int B, int H, int W, const float* x, const float* 
   GET("out_norm.scale", &out_norm, c.width[0]);
   GET("patch_out.proj.weight", &patch_out_w, (int64_t)c.patch_h * c.patch_w * c.out_channels, c.width[0]);
 
+  if (std::is_same<T, bf16>::value && m->fuse_norm && cond_bs == 0 && m->fold_descs != nullptr)
+    if ((rc = launch_fold_norm_weights(m->fold_descs, m->n_fold, cond, st))) return rc;
+  m->ss_valid = false;
   T* cur = reinterpret_cast<T*>(ws.xs[0]);
   if ((rc = launch_patch_in<T>(x, sigma, sd, patch_in_w, cur, B, c.in_channels, H, W, c.patch_h, c.patch_w, c.width[0], st))) return rc;
   if ((rc = tap<T>(m, "patch_in", cur, (int64_t)B * h0 * w0 * c.width[0], st))) return rc;
@@ -424,6 +457,7 @@ int forward_impl(KdbModel* m, int B, int H, int W, const float* x, const float* 
       if ((rc = launch_merge_gather<T>(cur, mg, B, h, w, c.width[l], st))) return rc;
       if ((rc = linear<T>(mg, WSel<T>::merge(m, l), nxt, Mc, c.width[l + 1], 4 * c.width[l], GemmEpi{}, st))) return rc;
     }
+    m->ss_valid = false;
     h /= 2;
     w /= 2;
     if ((rc = tap<T>(m, "L" + std::to_string(l) + ".merge", nxt, (int64_t)B * h * w * c.width[l + 1], st))) return rc;
@@ -441,6 +475,8 @@ int forward_impl(KdbModel* m, int B, int H, int W, const float* x, const float* 
     e.hc = h;
     e.wc = w;
     e.C = c.width[l];
+    m->ss_valid = std::is_same<T, bf16>::value && m->fuse_norm && tc_gemm_emits_rowss((int64_t)B * h * w, 4 * c.width[l], c.width[l + 1], e);
+    if (m->ss_valid) e.ss_out = ws.rowss;
     if ((rc = linear<T>(cur, WSel<T>::split(m, l), up, (int64_t)B * h * w, 4 * c.width[l], c.width[l + 1], e, st))) return rc;
     h *= 2;
     w *= 2;
@@ -453,6 +489,8 @@ int forward_impl(KdbModel* m, int B, int H, int W, const float* x, const float* 
   if (std::is_same<T, bf16>::value && m->patch_out_wb != nullptr &&
       tc_patch_out_supported(c.width[0], c.out_channels, c.patch_h, c.patch_w, W)) {
     // out_norm as a row kernel, then the projection on the tensor core with un-patch + Karras combine in its epilogue
+    if (m->ss_valid && m->patch_out_wf != nullptr && c.width[0] % 128 == 0 && c.width[0] <= 128 * SS_PARTS)
+      return launch_patch_out_tc(reinterpret_cast<const bf16*>(cur), m->patch_out_wf, x, sigma, sd, out, B, H, W, c.width[0], st, ws.rowss);
     T* xn = reinterpret_cast<T*>(ws.xn);
     const int64_t M0 = (int64_t)B * h0 * w0;
     if ((rc = launch_rmsnorm<T>(cur, xn, out_norm, 0, M0, M0, c.width[0], st))) return rc;
@@ -538,6 +576,27 @@ int kdb_model_finalize(KdbModel* m, void* stream) {
     for (int l = n - 2; l >= 0; --l)
       for (auto& L : m->up[l]) L.exec_index = k++;
     m->n_layers = k;
+    // table of (weights -> folded copy) pairs for the fused RMSNorm path
+    std::vector<FoldDesc> descs;
+    auto add = [&](const LayerPlan& L) {
+      if (L.C % 8 != 0) return;
+      if (L.qkv_wf != nullptr && L.ada_attn >= 0) descs.push_back(FoldDesc{L.qkv_wb, L.qkv_wf, 3 * L.C, L.C, L.ada_attn});
+      if (L.up_wf != nullptr && L.up_wb_il != nullptr) descs.push_back(FoldDesc{L.up_wb_il, L.up_wf, 2 * L.dff, L.C, L.ada_ff});
+    };
+    for (int l = 0; l < n - 1; ++l)
+      for (auto& L : m->down[l]) add(L);
+    for (auto& L : m->mid) add(L);
+    for (int l = n - 2; l >= 0; --l)
+      for (auto& L : m->up[l]) add(L);
+    m->n_fold = (int)descs.size();
+    m->fold_descs = nullptr;
+    if (!descs.empty()) {
+      if ((rc = dev_alloc(m, &m->fold_descs, descs.size()))) return rc;
+      KDB_CUDA(cudaMemcpyAsync(m->fold_descs, descs.data(), descs.size() * sizeof(FoldDesc), cudaMemcpyHostToDevice, st));
+      KDB_CUDA(cudaStreamSynchronize(st));
+    }
+    const char* e = getenv("KDB200_NO_FUSED_NORM");
+    m->fuse_norm = !(e != nullptr && e[0] == '1');
   }
   for (int l = 0; l < n - 1; ++l) {
     GET("merges." + std::to_string(l) + ".proj.weight", &m->merge_w[l], c.width[l + 1], 4 * c.width[l]);
@@ -558,6 +617,18 @@ int kdb_model_finalize(KdbModel* m, void* stream) {
       if ((rc = dev_alloc(m, &m->patch_out_wb, (size_t)64 * C0))) return rc;
       KDB_CUDA(cudaMemsetAsync(m->patch_out_wb, 0, (size_t)64 * C0 * sizeof(bf16), st));
       if ((rc = launch_f32_to_bf16(tmp, m->patch_out_wb, (int64_t)Np * C0, st))) return rc;
+      m->patch_out_wf = nullptr;
+      if (C0 % 8 == 0) {   // out_norm.scale is a plain parameter: fold it once
+        const float* out_scale = nullptr;
+        GET("out_norm.scale", &out_scale, C0);
+        FoldDesc* d1 = nullptr;
+        if ((rc = dev_alloc(m, &m->patch_out_wf, (size_t)64 * C0))) return rc;
+        if ((rc = dev_alloc(m, &d1, 1))) return rc;
+        const FoldDesc hd{m->patch_out_wb, m->patch_out_wf, 64, C0, 0};
+        KDB_CUDA(cudaMemcpyAsync(d1, &hd, sizeof(FoldDesc), cudaMemcpyHostToDevice, st));
+        if ((rc = launch_fold_norm_weights(d1, 1, out_scale, st))) return rc;
+        KDB_CUDA(cudaStreamSynchronize(st));
+      }
     }
   }
   // conditioning weights

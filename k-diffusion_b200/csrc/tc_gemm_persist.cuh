@@ -174,6 +174,18 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
       const int m0 = (tile / n_tiles_n) * BM, n0 = (tile % n_tiles_n) * P_BN;
       const int64_t m = (int64_t)m0 + row;
       const uint32_t acc = (uint32_t)grp, use = it >> 1;
+      // fused RMSNorm (consumer side): the producer of x left sum(x^2) of every token, one slot per 128 channels
+      float rstd = 1.f;
+      if (p.ss_in != nullptr) {
+        const float4* sp = reinterpret_cast<const float4*>(p.ss_in + (m < p.M ? m : 0) * SS_PARTS);
+        const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
+        const int parts = p.K >> 7;
+        float ssum = s0.x;
+        if (parts > 1) ssum += s0.y;
+        if (parts > 2) ssum += s0.z + s0.w;
+        if (parts > 4) ssum += (s1.x + s1.y) + (s1.z + s1.w);
+        rstd = rsqrtf(ssum / (float)p.K + 1e-6f);
+      }
       // QKV: the RoPE table row does not depend on the accumulator -> fetch it before waiting for the MMA
       float4 cs[2][8];
       if constexpr (EPI == TCE_QKV) {
@@ -197,6 +209,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
       tc::mbar_wait(&bars->tmem_full[acc], use & 1u);
       tc::tc_fence_after();
       if (issuer) KDB_TRACE(7);
+      float ss_acc[4] = {0.f, 0.f, 0.f, 0.f};   // producer side: sum of squares of the row this thread writes
       if constexpr (RES) tc::mbar_wait(&bars->resid_full[grp], use & 1u);
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
@@ -215,6 +228,15 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
           tc::mbar_arrive(&bars->tmem_empty[acc]);
         }
         if (issuer) KDB_TRACE(8 + g);
+        if (p.ss_in != nullptr) {
+          // fused RMSNorm row scale.  q and k are cosine-normalised afterwards (scale invariant): only v needs it.
+          bool apply = true;
+          if constexpr (EPI == TCE_QKV) apply = (n0 + g * 64) >= 2 * p.C;
+          if (apply) {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) v[i] *= rstd;
+          }
+        }
         // Epilogue arithmetic stays in fp32 and is rounded to bf16 once, at the pack (a K=128 tile leaves ~4 ALU
         // instructions per output element before the epilogue, not the tensor pipe, sets the pace).
         if constexpr (EPI == TCE_GEGLU) {
@@ -244,6 +266,17 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
                   v[j * 8 + t * 2] += lo;
                   v[j * 8 + t * 2 + 1] += hi;
                 }
+              }
+            }
+          }
+          if constexpr (RES) {
+            if (p.ss_out != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 64; i += 4) {
+                ss_acc[0] = fmaf(v[i], v[i], ss_acc[0]);
+                ss_acc[1] = fmaf(v[i + 1], v[i + 1], ss_acc[1]);
+                ss_acc[2] = fmaf(v[i + 2], v[i + 2], ss_acc[2]);
+                ss_acc[3] = fmaf(v[i + 3], v[i + 3], ss_acc[3]);
               }
             }
           }
@@ -279,6 +312,19 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
             *reinterpret_cast<uint4*>(cg + tc::sw128_offset(row, j)) =
                 make_uint4(tc::pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]), tc::pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]),
                            tc::pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]), tc::pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]));
+        }
+      }
+      if constexpr (RES) {
+        if (p.ss_out != nullptr && m < p.M) {     // statistics of the NEW residual stream for the next fused RMSNorm
+          const float ssv = (ss_acc[0] + ss_acc[1]) + (ss_acc[2] + ss_acc[3]);
+          if constexpr (EPI == TCE_SPLIT) {       // coarse token m, quadrant qd -> fine token
+            const int qd = n0 / p.Cf, e0 = n0 - qd * p.Cf;
+            const int64_t bhy = m / p.wc, wx = m - bhy * p.wc;
+            const int64_t fine = (2 * bhy + (qd >> 1)) * (2 * (int64_t)p.wc) + 2 * wx + (qd & 1);
+            p.ss_out[fine * SS_PARTS + (e0 >> 7)] = ssv;
+          } else {
+            p.ss_out[m * SS_PARTS + (n0 >> 7)] = ssv;
+          }
         }
       }
       if (issuer) KDB_TRACE(10);

@@ -82,6 +82,8 @@ struct TcParams {
   const float* sigma;
   float sd;
   int H, Wimg, th, tw;
+  const float* ss_in;    // fused RMSNorm (consumer): A = raw x, W carries the channel scale; [M, SS_PARTS] sums of squares of x
+  float* ss_out;         // RESID / SPLIT (producer): sums of squares of the rows written, for the next fused RMSNorm
   int a_merge, mwc, mC;  // A operand gathered from fine tokens (TokenMerge): coarse grid width, fine channels
   int box_w, box_h;      // 5-D TMA boxes of merge / split: 128 rows = box_h x box_w coarse tokens
   long long* trace;      // debug: per-tile clock64 stamps of CTA 0 (KDB200_GEMM_TRACE=1), else nullptr
@@ -228,6 +230,18 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         for (int i = 0; i < 32; ++i) { v[i] = t0[i]; v[32 + i] = t1[i]; }
       }
       if (m < p.M) {
+        if (p.ss_in != nullptr) {   // fused out_norm: A is the raw residual stream, W carries the channel scale
+          const float4* sp = reinterpret_cast<const float4*>(p.ss_in + m * SS_PARTS);
+          const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
+          const int parts = p.K >> 7;
+          float ssum = s0.x;
+          if (parts > 1) ssum += s0.y;
+          if (parts > 2) ssum += s0.z + s0.w;
+          if (parts > 4) ssum += (s1.x + s1.y) + (s1.z + s1.w);
+          const float rstd = rsqrtf(ssum / (float)p.K + 1e-6f);
+#pragma unroll
+          for (int i = 0; i < 48; ++i) v[i] *= rstd;
+        }
         const int per = p.th * p.tw;
         const int b = (int)(m / per);
         const int r = (int)(m - (int64_t)b * per);
@@ -450,6 +464,8 @@ static bool g_tc_disabled = [] {
 
 bool tc_gemm_supported(int64_t M, int N, int K, const GemmEpi& epi) {
   if (g_tc_disabled || !shape_ok(M, N, K)) return false;
+  if (epi.ss_in != nullptr && (N % 128 != 0 || K % 128 != 0 || K > 128 * SS_PARTS || (epi.mode != EPI_STORE && epi.mode != EPI_QKV_ROPE) || epi.mC > 0))
+    return false;
   if (epi.mC > 0) {   // TokenMerge gather folded into the A loads: persistent kernel only, plain store epilogue
     int bw, bh;
     if (epi.mode != EPI_STORE || N % 128 != 0 || epi.mC % 64 != 0 || K != 4 * epi.mC || M % epi.mwc != 0 || !quad_box(epi.mwc, &bw, &bh)) return false;
@@ -457,6 +473,20 @@ bool tc_gemm_supported(int64_t M, int N, int K, const GemmEpi& epi) {
   if (epi.mode == EPI_SPLIT_LERP) return epi.C % 32 == 0 && N == 4 * epi.C;
   if (epi.mode == EPI_QKV_ROPE) return N == 3 * epi.C && epi.C % 64 == 0 && epi.nh * 64 == epi.C && epi.rope != nullptr;
   return epi.mode == EPI_STORE || epi.mode == EPI_RESID;
+}
+
+// true when the RESID / SPLIT GEMM of this shape runs on the persistent kernel, which can leave sum(x^2) of every row it writes
+bool tc_gemm_emits_rowss(int64_t M, int N, int K, const GemmEpi& epi) {
+  if (!tc_gemm_supported(M, N, K, epi)) return false;
+  TcParams p{};
+  p.N = N;
+  if (!use_persistent(p)) return false;
+  if (epi.mode == EPI_RESID) return N <= 128 * SS_PARTS;
+  if (epi.mode == EPI_SPLIT_LERP) {
+    int bw, bh;
+    return epi.C % P_BN == 0 && epi.C <= 128 * SS_PARTS && M % epi.wc == 0 && quad_box(epi.wc, &bw, &bh);
+  }
+  return false;
 }
 
 int launch_gemm_tc(const bf16* A, const bf16* W, bf16* C, int64_t M, int N, int K, const GemmEpi& epi, cudaStream_t st) {
@@ -469,6 +499,10 @@ int launch_gemm_tc(const bf16* A, const bf16* W, bf16* C, int64_t M, int N, int 
   p.N = N;
   p.K = K;
   p.stages = pick_stages(K, epi.mode == EPI_RESID);
+  p.ss_in = epi.ss_in;
+  p.ss_out = epi.ss_out;
+  KDB_REQUIRE(epi.ss_in == nullptr || tc_gemm_supported(M, N, K, epi), KDB_ERR_UNSUPPORTED, "gemm_tc: fused-norm geometry not supported");
+  KDB_REQUIRE(epi.ss_out == nullptr || tc_gemm_emits_rowss(M, N, K, epi), KDB_ERR_UNSUPPORTED, "gemm_tc: this shape cannot emit row statistics");
   if (epi.mC > 0) {
     KDB_REQUIRE(tc_gemm_supported(M, N, K, epi), KDB_ERR_UNSUPPORTED, "gemm_tc: token-merge geometry not supported");
     p.a_merge = 1;
@@ -508,8 +542,10 @@ bool tc_patch_out_supported(int C0, int Cout, int ph, int pw, int Wimg) {
 }
 
 int launch_patch_out_tc(const bf16* xn, const bf16* W_pad, const float* x_in, const float* sigma, float sigma_data, float* out, int B, int H,
-                        int Wimg, int C0, cudaStream_t st) {
+                        int Wimg, int C0, cudaStream_t st, const float* ss_in) {
+  KDB_REQUIRE(ss_in == nullptr || (C0 % 128 == 0 && C0 <= 128 * SS_PARTS), KDB_ERR_UNSUPPORTED, "patch_out_tc: fused norm needs C0 %% 128 == 0");
   TcParams p{};
+  p.ss_in = ss_in;
   p.M = (int64_t)B * (H / 4) * (Wimg / 4);
   p.N = 64;
   p.K = C0;
@@ -526,11 +562,40 @@ int launch_patch_out_tc(const bf16* xn, const bf16* W_pad, const float* x_in, co
   return launch_tc<64, TCE_PATCHOUT>(xn, W_pad, p, st);
 }
 
-bool tc_gemm_geglu_supported(int64_t M, int N2, int K) { return !g_tc_disabled && shape_ok(M, N2, K) && N2 % 128 == 0; }
+bool tc_gemm_geglu_supported(int64_t M, int N2, int K, bool fused_norm) {
+  if (fused_norm && (K % 128 != 0 || K > 128 * SS_PARTS)) return false;
+  return !g_tc_disabled && shape_ok(M, N2, K) && N2 % 128 == 0;
+}
 
-int launch_gemm_tc_geglu(const bf16* A, const bf16* W_il, bf16* out, int64_t M, int N2, int K, cudaStream_t st) {
-  KDB_REQUIRE(shape_ok(M, N2, K) && N2 % 128 == 0, KDB_ERR_BAD_SHAPE, "gemm_tc_geglu: unsupported shape");
+__global__ void __launch_bounds__(256) fold_norm_weights_kernel(const FoldDesc* __restrict__ descs, const float* __restrict__ cond) {
+  const FoldDesc d = descs[blockIdx.y];
+  const int64_t chunks = (int64_t)d.rows * d.K / 8;
+  const float* g = cond + d.ada_off;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < chunks; i += (int64_t)gridDim.x * 256) {
+    const int k0 = (int)((i * 8) % d.K);
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(d.src) + i);
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float lo = __uint_as_float(w[t] << 16) * __ldg(g + k0 + 2 * t), hi = __uint_as_float(w[t] & 0xffff0000u) * __ldg(g + k0 + 2 * t + 1);
+      o[t] = tc::pack_bf16x2(lo, hi);
+    }
+    reinterpret_cast<uint4*>(d.dst)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+int launch_fold_norm_weights(const FoldDesc* descs_dev, int n_desc, const float* cond_row, cudaStream_t st) {
+  if (n_desc <= 0) return 0;
+  fold_norm_weights_kernel<<<dim3(48, (unsigned)n_desc), 256, 0, st>>>(descs_dev, cond_row);
+  KDB_LAUNCH_CHECK(F_FUSED_NORM, st);
+  return 0;
+}
+
+int launch_gemm_tc_geglu(const bf16* A, const bf16* W_il, bf16* out, int64_t M, int N2, int K, cudaStream_t st, const float* ss_in) {
+  KDB_REQUIRE(tc_gemm_geglu_supported(M, N2, K, ss_in != nullptr), KDB_ERR_BAD_SHAPE, "gemm_tc_geglu: unsupported shape");
   TcParams p{};
+  p.ss_in = ss_in;
   p.out = out;
   p.M = M;
   p.N = N2;

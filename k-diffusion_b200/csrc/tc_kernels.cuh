@@ -6,16 +6,29 @@ namespace kdb {
 
 // C[M,N] = A[M,K] W[N,K]^T (+ epilogue), bf16 operands staged by TMA, fp32 accumulators in TMEM.
 bool tc_gemm_supported(int64_t M, int N, int K, const GemmEpi& epi);
+// Fused RMSNorm: a RESID / SPLIT_LERP GEMM can leave sum(x^2) of every row it writes ([rows, SS_PARTS] fp32, one slot per 128
+// channels) and a STORE / QKV_ROPE / GEGLU GEMM whose A operand is that x can apply 1/rms in its epilogue (GemmEpi::ss_out / ss_in).
+constexpr int SS_PARTS = 8;
+bool tc_gemm_emits_rowss(int64_t M, int N, int K, const GemmEpi& epi);
 int launch_gemm_tc(const bf16* A, const bf16* W, bf16* C, int64_t M, int N, int K, const GemmEpi& epi, cudaStream_t st);
 
 // up_proj with the GEGLU fused into the epilogue; W rows interleaved 8 value / 8 gate (engine.cu).
-bool tc_gemm_geglu_supported(int64_t M, int N2, int K);
-int launch_gemm_tc_geglu(const bf16* A, const bf16* W_il, bf16* out, int64_t M, int N2, int K, cudaStream_t st);
+bool tc_gemm_geglu_supported(int64_t M, int N2, int K, bool fused_norm = false);
+int launch_gemm_tc_geglu(const bf16* A, const bf16* W_il, bf16* out, int64_t M, int N2, int K, cudaStream_t st, const float* ss_in = nullptr);
 
-// patch_out (4x4 patches, 3 channels): xn bf16 [M, C0] x W_pad bf16 [64, C0] -> fp32 NCHW with the Karras combine fused
+// W'[n,k] = W[n,k] * g[k] for a table of weight matrices (AdaRMSNorm channel scale folded into the consumer weights)
+struct FoldDesc {
+  const bf16* src;
+  bf16* dst;
+  int rows, K, ada_off;
+};
+int launch_fold_norm_weights(const FoldDesc* descs_dev, int n_desc, const float* cond_row, cudaStream_t st);
+
+// patch_out (4x4 patches, 3 channels): xn bf16 [M, C0] x W_pad bf16 [64, C0] -> fp32 NCHW with the Karras combine fused.
+// ss_in != nullptr: xn is the RAW residual stream, W_pad carries out_norm.scale and the epilogue applies 1/rms per token.
 bool tc_patch_out_supported(int C0, int Cout, int ph, int pw, int Wimg);
 int launch_patch_out_tc(const bf16* xn, const bf16* W_pad, const float* x_in, const float* sigma, float sigma_data, float* out, int B, int H,
-                        int Wimg, int C0, cudaStream_t st);
+                        int Wimg, int C0, cudaStream_t st, const float* ss_in = nullptr);
 
 bool tc_attention_supported(int h, int w, int nh, int e, int attn_type, int attn_param);
 int launch_attention_tc(const bf16* qkv, bf16* out, int B, int h, int w, int nh, int e, int attn_type, int attn_param, int shift,
