@@ -647,14 +647,43 @@ template int launch_patch_out<bf16>(const bf16*, const float*, const float*, con
 // Conditioning: FourierFeatures -> in-proj -> MappingNetwork -> concatenated AdaRMSNorm projections.
 // One CTA (8 warps) per row; warp-per-output matvecs, weights streamed from L2.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void block_matvec(const float* __restrict__ W, const float* vin, float* vout, int n_out, int n_in, bool accumulate) {
+// vout[o] = (accumulate ? vout[o] : 0) + bias + W[o, :] . vin for o in [o_begin, o_end).  One warp per output, four outputs
+// in flight per warp and 16-byte weight loads, so a warp keeps 8+ independent L2 requests outstanding (the chain of
+// matvecs is latency bound, not bandwidth bound).
+__device__ __forceinline__ void block_matvec(const float* __restrict__ W, const float* vin, float* vout, int o_begin, int o_end, int n_in,
+                                             bool accumulate, float bias = 0.f) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int o = warp; o < n_out; o += nw) {
-    const float* wr = W + (int64_t)o * n_in;
-    float s = 0.f;
-    for (int k = lane; k < n_in; k += 32) s = fmaf(__ldg(wr + k), vin[k], s);
-    s = warp_sum(s);
-    if (lane == 0) vout[o] = accumulate ? vout[o] + s : s;
+  const bool vec = (n_in % 128 == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
+  for (int o = o_begin + warp; o < o_end; o += 4 * nw) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    if (vec) {
+      for (int k = lane * 4; k < n_in; k += 128) {
+        const float4 x = *reinterpret_cast<const float4*>(vin + k);
+        float4 wv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int oo = o + u * nw;
+          wv[u] = oo < o_end ? __ldg(reinterpret_cast<const float4*>(W + (int64_t)oo * n_in + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) s[u] = fmaf(wv[u].x, x.x, fmaf(wv[u].y, x.y, fmaf(wv[u].z, x.z, fmaf(wv[u].w, x.w, s[u]))));
+      }
+    } else {
+      for (int k = lane; k < n_in; k += 32) {
+        const float x = vin[k];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int oo = o + u * nw;
+          if (oo < o_end) s[u] = fmaf(__ldg(W + (int64_t)oo * n_in + k), x, s[u]);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int oo = o + u * nw;
+      const float t = warp_sum(s[u]);
+      if (lane == 0 && oo < o_end) vout[oo] = (accumulate ? vout[oo] : 0.f) + bias + t;
+    }
   }
 }
 
@@ -682,7 +711,8 @@ __device__ __forceinline__ void block_rmsnorm(const float* x, float* y, const fl
 __global__ void __launch_bounds__(256) conditioning_kernel(const CondWeights w, const float* __restrict__ sigma,
                                                            const float* __restrict__ aug, const int64_t* __restrict__ cls,
                                                            const float* __restrict__ mcond, float* __restrict__ out, int64_t out_stride) {
-  extern __shared__ float sm[];
+  extern __shared__ float4 cond_sm4[];          // 16-byte aligned: block_matvec reads its input vector as float4
+  float* sm = reinterpret_cast<float*>(cond_sm4);
   const int mw = w.mw, dff = w.dff;
   float* ff = sm;              // [mw]   fourier features
   float* emb = ff + mw;        // [mw]   summed embedding / residual stream
@@ -704,7 +734,7 @@ __global__ void __launch_bounds__(256) conditioning_kernel(const CondWeights w, 
     ff[half + j] = s;
   }
   __syncthreads();
-  block_matvec(w.time_in, ff, emb, mw, mw, false);
+  block_matvec(w.time_in, ff, emb, 0, mw, mw, false);
   __syncthreads();
   // augmentation embedding (zeros when aug_cond is None, :736-737)
   for (int j = threadIdx.x; j < half; j += blockDim.x) {
@@ -717,7 +747,7 @@ __global__ void __launch_bounds__(256) conditioning_kernel(const CondWeights w, 
     ff[half + j] = s;
   }
   __syncthreads();
-  block_matvec(w.aug_in, ff, emb, mw, mw, true);
+  block_matvec(w.aug_in, ff, emb, 0, mw, mw, true);
   __syncthreads();
   if (w.class_emb != nullptr) {
     const int64_t ci = cls[row];
@@ -726,7 +756,7 @@ __global__ void __launch_bounds__(256) conditioning_kernel(const CondWeights w, 
   if (w.mcond_in != nullptr) {
     for (int j = threadIdx.x; j < w.mcond_dim; j += blockDim.x) mc[j] = mcond[(int64_t)row * w.mcond_dim + j];
     __syncthreads();
-    block_matvec(w.mcond_in, mc, emb, mw, w.mcond_dim, true);
+    block_matvec(w.mcond_in, mc, emb, 0, mw, w.mcond_dim, true);
   }
   __syncthreads();
 
@@ -734,39 +764,34 @@ __global__ void __launch_bounds__(256) conditioning_kernel(const CondWeights w, 
   block_rmsnorm(emb, emb, w.in_norm, mw, red);
   for (int l = 0; l < w.depth; ++l) {
     block_rmsnorm(emb, xn, w.blk_norm[l], mw, red);
-    block_matvec(w.blk_up[l], xn, up, 2 * dff, mw, false);
+    block_matvec(w.blk_up[l], xn, up, 0, 2 * dff, mw, false);
     __syncthreads();
     for (int i = threadIdx.x; i < dff; i += blockDim.x) {
       const float g = up[dff + i];
       up[i] = up[i] * (0.5f * g * (1.f + erff(g * 0.70710678118654752440f)));
     }
     __syncthreads();
-    block_matvec(w.blk_down[l], up, emb, mw, dff, true);
+    block_matvec(w.blk_down[l], up, emb, 0, mw, dff, true);
     __syncthreads();
   }
   block_rmsnorm(emb, xn, w.out_norm, mw, red);
 
-  // every AdaRMSNorm: scale = Linear(cond) + 1   (:166)
+  // every AdaRMSNorm: scale = Linear(cond) + 1   (:166).  The CTAs of one row (gridDim.y) share the outputs; each repeats the
+  // (short) mapping network so that no second launch or grid-wide hand-off is needed.
   float* orow = out + (int64_t)row * out_stride;
-  {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    for (int o = warp; o < w.ada_total; o += nw) {
-      const float* wr = w.ada_cat + (int64_t)o * mw;
-      float s = 0.f;
-      for (int k = lane; k < mw; k += 32) s = fmaf(__ldg(wr + k), xn[k], s);
-      s = warp_sum(s);
-      if (lane == 0) orow[o] = s + 1.f;
-    }
-  }
-  for (int j = threadIdx.x; j < mw; j += blockDim.x) orow[w.ada_total + j] = xn[j];   // cond itself (debug / taps)
+  const int per = (w.ada_total + (int)gridDim.y - 1) / (int)gridDim.y;
+  const int o0 = (int)blockIdx.y * per, o1 = min(w.ada_total, o0 + per);
+  block_matvec(w.ada_cat, xn, orow, o0, o1, mw, false, 1.f);
+  if (blockIdx.y == 0)
+    for (int j = threadIdx.x; j < mw; j += blockDim.x) orow[w.ada_total + j] = xn[j];   // cond itself (debug / taps)
 }
 
 int launch_conditioning(const CondWeights& w, int rows, const float* sigma, const float* aug, const int64_t* cls, const float* mcond,
                         float* out, int64_t out_stride, cudaStream_t st) {
-  KDB_REQUIRE(w.mw % 2 == 0 && w.depth <= 8, KDB_ERR_UNSUPPORTED, "conditioning: mapping width must be even, depth <= 8");
+  KDB_REQUIRE(w.mw % 4 == 0 && w.dff % 2 == 0 && w.depth <= 8, KDB_ERR_UNSUPPORTED, "conditioning: mapping width must be a multiple of 4, depth <= 8");
   const size_t smem = sizeof(float) * (size_t)(3 * w.mw + 2 * w.dff + 32 + w.mcond_dim);
   KDB_REQUIRE(smem <= 48 * 1024, KDB_ERR_UNSUPPORTED, "conditioning: mapping network too wide");
-  conditioning_kernel<<<rows, 256, smem, st>>>(w, sigma, aug, cls, mcond, out, out_stride);
+  conditioning_kernel<<<dim3((unsigned)rows, 4), 256, smem, st>>>(w, sigma, aug, cls, mcond, out, out_stride);
   KDB_LAUNCH_CHECK(F_COND, st);
   return 0;
 }

@@ -28,7 +28,7 @@ constexpr size_t P_SMEM_LIMIT = 227 * 1024;
 struct PersistBars {
   uint64_t full[P_MAX_STAGES], empty[P_MAX_STAGES];
   uint64_t tmem_full[2], tmem_empty[2];
-  uint64_t resid_full[2], resid_empty, b_full;   // resid_full per epilogue group: a waiter must observe every phase of its barrier
+  uint64_t resid_full[2], b_full;   // resid_full per epilogue group: a waiter must observe every phase of its barrier
   uint32_t tmem;
 };
 
@@ -40,6 +40,7 @@ struct PersistBars {
 
 struct PersistCfg {
   int stages, b_res, sc_bufs;
+  int nb;   // weight-resident mode: n-blocks kept resident per CTA; every A tile is loaded once and used for all of them
 };
 
 template <int EPI>
@@ -48,19 +49,49 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
                                                                 const TcParams p, const PersistCfg cfg) {
   extern __shared__ uint8_t smem_raw[];
   constexpr uint32_t IDESC = tc::idesc_bf16(BM, P_BN);
-  constexpr bool RES = EPI == TCE_RESID || EPI == TCE_SPLIT;   // a second [128 x 128] operand tile (residual / skip) is staged by TMA
+  // RESID / SPLIT: the [128 x 128] residual / skip tile is loaded by TMA straight INTO the group's output staging tile and the
+  // epilogue adds in place, so it is double-buffered with the staging tiles and needs no shared memory of its own.
+  constexpr bool RES = EPI == TCE_RESID || EPI == TCE_SPLIT;
   const int nkb = p.K / BK;
   const int stage_bytes = cfg.b_res ? A_STAGE_BYTES : A_STAGE_BYTES + P_B_TILE_BYTES;
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sB = base;                                                            // resident weight block (b_res)
-  uint8_t* sStage = sB + (cfg.b_res ? (size_t)nkb * P_B_TILE_BYTES : 0);
+  const int nb = cfg.b_res ? cfg.nb : 1;
+  uint8_t* sStage = sB + (cfg.b_res ? (size_t)nb * nkb * P_B_TILE_BYTES : 0);
   uint8_t* sC = sStage + (size_t)cfg.stages * stage_bytes;                       // 1 or 2 staging tiles
-  uint8_t* sR = sC + (size_t)cfg.sc_bufs * P_OUT_BYTES;                          // residual tile (RESID only)
-  PersistBars* bars = reinterpret_cast<PersistBars*>(sR + (RES ? P_OUT_BYTES : 0));
+  PersistBars* bars = reinterpret_cast<PersistBars*>(sC + (size_t)cfg.sc_bufs * P_OUT_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles_n = p.N / P_BN;
-  const int n_tiles = n_tiles_n * (int)((p.M + BM - 1) / BM);
+  const int m_tiles = (int)((p.M + BM - 1) / BM);
+  const int n_tiles = n_tiles_n * m_tiles;
+  // Work list of this CTA, as a sequence of 128 x 128 output tiles `it` = 0 .. n_local-1.
+  //  streaming mode : tile = blockIdx.x + it * gridDim.x over the (m, n) grid, both operands loaded per tile
+  //  resident mode  : the CTA owns n-blocks [ng*nb, ng*nb+nb) (weights resident) and walks m-tiles mw, mw+G, ...; the nb tiles of
+  //                   one m-tile are consecutive and share ONE load of the A tile (A leaves L2 once per nb*128 output columns)
+  int n_local, ng = 0, mw = 0, G = 1;
+  if (cfg.b_res) {
+    const int n_groups = n_tiles_n / nb;
+    ng = (int)blockIdx.x % n_groups;
+    mw = (int)blockIdx.x / n_groups;
+    G = (int)gridDim.x / n_groups;
+    n_local = mw < m_tiles ? ((m_tiles - 1 - mw) / G + 1) * nb : 0;
+  } else {
+    n_local = (int)blockIdx.x < n_tiles ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  }
+  auto coords = [&](uint32_t it, int& m0, int& n0, int& j) {
+    if (cfg.b_res) {
+      const int i = (int)it / nb;
+      j = (int)it - i * nb;
+      m0 = (mw + i * G) * BM;
+      n0 = (ng * nb + j) * P_BN;
+    } else {
+      const int tile = (int)blockIdx.x + (int)it * (int)gridDim.x;
+      j = 0;
+      m0 = (tile / n_tiles_n) * BM;
+      n0 = (tile % n_tiles_n) * P_BN;
+    }
+  };
 
   if (threadIdx.x == 0) {
     tc::tma_prefetch_desc(&tma);
@@ -77,7 +108,6 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
     }
     tc::mbar_init(&bars->resid_full[0], 1);
     tc::mbar_init(&bars->resid_full[1], 1);
-    tc::mbar_init(&bars->resid_empty, 1);
     tc::mbar_init(&bars->b_full, 1);
     tc::fence_barrier_init();
   }
@@ -89,16 +119,21 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
 
   if (warp == 0) {
     if (tc::elect_one()) {
-      if (cfg.b_res && (int)blockIdx.x < n_tiles) {       // this CTA's n-block never changes (gridDim.x % n_tiles_n == 0)
-        const int n0 = ((int)blockIdx.x % n_tiles_n) * P_BN;
-        tc::mbar_arrive_expect_tx(&bars->b_full, (uint32_t)nkb * P_B_TILE_BYTES);
-        for (int kb = 0; kb < nkb; ++kb) tc::tma_load_2d(sB + (size_t)kb * P_B_TILE_BYTES, &tmb, &bars->b_full, kb * BK, n0);
+      if (cfg.b_res && n_local > 0) {       // this CTA's n-blocks never change
+        tc::mbar_arrive_expect_tx(&bars->b_full, (uint32_t)(nb * nkb) * P_B_TILE_BYTES);
+        for (int j = 0; j < nb; ++j)
+          for (int kb = 0; kb < nkb; ++kb)
+            tc::tma_load_2d(sB + (size_t)(j * nkb + kb) * P_B_TILE_BYTES, &tmb, &bars->b_full, kb * BK, (ng * nb + j) * P_BN);
       }
-      uint32_t kc = 0, it = 0;      // k-blocks issued so far (ring position), tiles so far
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int m0 = (tile / n_tiles_n) * BM, n0 = (tile % n_tiles_n) * P_BN;
-        for (int kb = 0; kb < nkb; ++kb, ++kc) {
-          const uint32_t s = kc % (uint32_t)cfg.stages, ph = (kc / (uint32_t)cfg.stages) & 1u;
+      uint32_t s = 0, ph = 0;      // ring slot / phase (carried incrementally: no division in the loop)
+      int jj = 0;
+      for (uint32_t it = 0; it < (uint32_t)n_local; ++it) {
+        const bool load = jj == 0;          // otherwise the A tile of this m-tile is already in the ring
+        if (++jj == nb) jj = 0;
+        if (!load) continue;
+        int m0, n0, j;
+        coords(it, m0, n0, j);
+        for (int kb = 0; kb < nkb; ++kb) {
           tc::mbar_wait(&bars->empty[s], ph ^ 1u);
           tc::mbar_arrive_expect_tx(&bars->full[s], (uint32_t)stage_bytes);
           uint8_t* a = sStage + (size_t)s * stage_bytes;
@@ -109,49 +144,68 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
             tc::tma_load_2d(a, &tma, &bars->full[s], kb * BK, m0);
           }
           if (!cfg.b_res) tc::tma_load_2d(a + A_STAGE_BYTES, &tmb, &bars->full[s], kb * BK, n0);
-        }
-        KDB_TRACE(0);
-        if (RES) {   // needed only by this tile's epilogue: issued after the operands so it never delays the MMA
-          tc::mbar_wait(&bars->resid_empty, (it & 1u) ^ 1u);
-          uint64_t* rf = &bars->resid_full[it & 1u];       // the group that owns tile `it`
-          tc::mbar_arrive_expect_tx(rf, P_OUT_BYTES);
-          if constexpr (EPI == TCE_SPLIT) {   // skip tensor: fine tokens of quadrant (nh, nw) = n0 / Cf, channels e0..e0+127
-            const int qd = n0 / p.Cf, e0 = n0 - qd * p.Cf;
-            const int wx0 = p.box_h == 1 ? m0 % p.wc : 0, bhy0 = m0 / p.wc;
-            tc::tma_load_5d(sR, &tmr, rf, e0, qd & 1, wx0, qd >> 1, bhy0);
-            tc::tma_load_5d(sR + SUB_TILE_BYTES, &tmr, rf, e0 + 64, qd & 1, wx0, qd >> 1, bhy0);
-          } else {
-            tc::tma_load_2d(sR, &tmr, rf, n0, m0);
-            tc::tma_load_2d(sR + SUB_TILE_BYTES, &tmr, rf, n0 + 64, m0);
+          if (++s == (uint32_t)cfg.stages) {
+            s = 0;
+            ph ^= 1u;
           }
         }
+        KDB_TRACE(0);
       }
     }
   } else if (warp == 1) {
     if (tc::elect_one()) {
-      uint32_t kc = 0, it = 0;
-      if (cfg.b_res && (int)blockIdx.x < n_tiles) tc::mbar_wait(&bars->b_full, 0);
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const uint32_t acc = it & 1u, use = it >> 1;                // use-th time this accumulator is filled
+      // This thread shares its scheduler with two epilogue warps and is rarely the one selected, so every instruction between
+      // two tcgen05.mma costs tens of cycles (measured: ~500 cycles per k-block with runtime divisions in the loop, against 256
+      // cycles of tensor work).  Ring position, phase and n-block index are therefore carried incrementally -- no division,
+      // no modulo, addresses by addition.
+      if (cfg.b_res && n_local > 0) tc::mbar_wait(&bars->b_full, 0);
+      const uint32_t stage_base = tc::smem_u32(sStage), b_base = tc::smem_u32(sB);
+      const uint32_t n_stages = (uint32_t)cfg.stages, sbytes = (uint32_t)stage_bytes;
+      const bool bres = cfg.b_res != 0;
+      uint32_t s0 = 0, ph0 = 0;              // ring slot / phase of the current m-tile's first k-block
+      uint32_t a0 = stage_base;              // its shared-memory address
+      uint32_t j = 0;                        // n-block index inside the m-tile
+      uint32_t bj = b_base;                  // resident weights of n-block j
+      for (uint32_t it = 0; it < (uint32_t)n_local; ++it) {
+        const uint32_t acc = it & 1u;
         KDB_TRACE(1);
-        tc::mbar_wait(&bars->tmem_empty[acc], (use & 1u) ^ 1u);     // epilogue drained it
+        tc::mbar_wait(&bars->tmem_empty[acc], ((it >> 1) & 1u) ^ 1u);     // epilogue drained it
         tc::tc_fence_after();
         KDB_TRACE(2);
         const uint32_t d = tmem + acc * P_BN;
-        for (int kb = 0; kb < nkb; ++kb, ++kc) {
-          const uint32_t s = kc % (uint32_t)cfg.stages, ph = (kc / (uint32_t)cfg.stages) & 1u;
-          tc::mbar_wait(&bars->full[s], ph);
-          tc::tc_fence_after();
-          const uint32_t a_addr = tc::smem_u32(sStage + (size_t)s * stage_bytes);
-          const uint32_t b_addr = cfg.b_res ? tc::smem_u32(sB + (size_t)kb * P_B_TILE_BYTES) : a_addr + A_STAGE_BYTES;
-          const uint64_t adesc = tc::smem_desc_k_sw128(a_addr);
-          const uint64_t bdesc = tc::smem_desc_k_sw128(b_addr);
+        const bool first = j == 0, last = j + 1 == (uint32_t)nb;
+        uint32_t ss = s0, pp = ph0, aa = a0, bb = bres ? bj : a0 + A_STAGE_BYTES;
+        for (int kb = 0; kb < nkb; ++kb) {
+          if (first) {                                              // first use of this A k-block
+            tc::mbar_wait(&bars->full[ss], pp);
+            tc::tc_fence_after();
+          }
+          const uint64_t adesc = tc::smem_desc_k_sw128(aa);
+          const uint64_t bdesc = tc::smem_desc_k_sw128(bb);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) tc::umma_bf16(d, adesc + 2ull * k, bdesc + 2ull * k, IDESC, (uint32_t)((kb | k) != 0));
-          tc::umma_commit(&bars->empty[s]);
+          if (last) tc::umma_commit(&bars->empty[ss]);              // last n-block of this m-tile: the stage may be refilled
+          aa += sbytes;
+          bb += bres ? (uint32_t)P_B_TILE_BYTES : sbytes;
+          if (++ss == n_stages) {
+            ss = 0;
+            pp ^= 1u;
+            aa = stage_base;
+            if (!bres) bb = stage_base + A_STAGE_BYTES;
+          }
         }
         tc::umma_commit(&bars->tmem_full[acc]);
         KDB_TRACE(3);
+        if (last) {
+          j = 0;
+          bj = b_base;
+          s0 = ss;
+          ph0 = pp;
+          a0 = aa;
+        } else {
+          ++j;
+          bj += (uint32_t)nkb * P_B_TILE_BYTES;
+        }
       }
     }
   } else {
@@ -168,10 +222,30 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
     uint8_t* ct = sC + (size_t)grp * P_OUT_BYTES;
     float facv = 0.f;
     if constexpr (EPI == TCE_SPLIT) facv = __ldg(p.fac);
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      if ((int)(it & 1u) != grp) continue;
-      const int m0 = (tile / n_tiles_n) * BM, n0 = (tile % n_tiles_n) * P_BN;
+    // residual / skip tile of `tile` -> this group's staging tile (issuer thread only; the staging tile must be free)
+    auto load_resid = [&](uint32_t it_) {
+      if constexpr (RES) {
+        int m0, n0, j_;
+        coords(it_, m0, n0, j_);
+        uint64_t* rf = &bars->resid_full[grp];
+        tc::mbar_arrive_expect_tx(rf, P_OUT_BYTES);
+        if constexpr (EPI == TCE_SPLIT) {   // skip tensor: fine tokens of quadrant (nh, nw) = n0 / Cf, channels e0..e0+127
+          const int qd = n0 / p.Cf, e0 = n0 - qd * p.Cf;
+          const int wx0 = p.box_h == 1 ? m0 % p.wc : 0, bhy0 = m0 / p.wc;
+          tc::tma_load_5d(ct, &tmr, rf, e0, qd & 1, wx0, qd >> 1, bhy0);
+          tc::tma_load_5d(ct + SUB_TILE_BYTES, &tmr, rf, e0 + 64, qd & 1, wx0, qd >> 1, bhy0);
+        } else {
+          tc::tma_load_2d(ct, &tmr, rf, n0, m0);
+          tc::tma_load_2d(ct + SUB_TILE_BYTES, &tmr, rf, n0 + 64, m0);
+        }
+      }
+    };
+    if constexpr (RES) {
+      if (issuer && grp < n_local) load_resid((uint32_t)grp);
+    }
+    for (uint32_t it = (uint32_t)grp; it < (uint32_t)n_local; it += 2) {
+      int m0, n0, j_;
+      coords(it, m0, n0, j_);
       const int64_t m = (int64_t)m0 + row;
       const uint32_t acc = (uint32_t)grp, use = it >> 1;
       // fused RMSNorm (consumer side): the producer of x left sum(x^2) of every token, one slot per 128 channels
@@ -202,9 +276,11 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
         }
       }
       if (issuer) KDB_TRACE(4);
-      if (issuer) tc::tma_store_wait_read();               // this group's previous store has finished READING the staging tile
-      if (issuer) KDB_TRACE(5);
-      tc::named_barrier_sync(1 + 2 * grp, 128);
+      if constexpr (!RES) {   // (RES: the residual load into the staging tile was issued after that wait; resid_full orders the writes)
+        if (issuer) tc::tma_store_wait_read();             // this group's previous store has finished READING the staging tile
+        if (issuer) KDB_TRACE(5);
+        tc::named_barrier_sync(1 + 2 * grp, 128);
+      }
       if (issuer) KDB_TRACE(6);
       tc::mbar_wait(&bars->tmem_full[acc], use & 1u);
       tc::tc_fence_after();
@@ -250,7 +326,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
           }
         } else {
           if constexpr (RES) {
-            const uint8_t* rt = sR + g * SUB_TILE_BYTES;
+            const uint8_t* rt = ct + g * SUB_TILE_BYTES;     // this thread reads and then overwrites only its own row
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const uint4 r4 = *reinterpret_cast<const uint4*>(rt + tc::sw128_offset(row, j));
@@ -332,7 +408,6 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
       tc::named_barrier_sync(2 + 2 * grp, 128);
       if (issuer) KDB_TRACE(11);
       if (issuer) {
-        if constexpr (RES) tc::mbar_arrive(&bars->resid_empty);      // the whole group has consumed the residual tile
         if constexpr (EPI == TCE_GEGLU) {
           tc::tma_store_2d(&tmc, ct, n0 / 2, m0);
         } else if constexpr (EPI == TCE_SPLIT) {
@@ -346,6 +421,12 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
         }
         tc::tma_store_commit();
         KDB_TRACE(12);
+        if constexpr (RES) {   // prefetch the residual of this group's next tile as soon as the store has drained the staging tile
+          if (it + 2 < (uint32_t)n_local) {
+            tc::tma_store_wait_read();
+            load_resid(it + 2);
+          }
+        }
       }
     }
     if (issuer) tc::tma_store_wait_read();
@@ -369,24 +450,38 @@ inline int num_sms() {
 
 inline size_t persist_smem(int nkb, bool resid, const PersistCfg& c) {
   const size_t stage = c.b_res ? A_STAGE_BYTES : A_STAGE_BYTES + P_B_TILE_BYTES;
-  return (c.b_res ? (size_t)nkb * P_B_TILE_BYTES : 0) + (size_t)c.stages * stage + (size_t)c.sc_bufs * P_OUT_BYTES + (resid ? P_OUT_BYTES : 0) +
-         sizeof(PersistBars) + 1024;
+  (void)resid;   // the residual tile shares the output staging tiles
+  return (c.b_res ? (size_t)c.nb * nkb * P_B_TILE_BYTES : 0) + (size_t)c.stages * stage + (size_t)c.sc_bufs * P_OUT_BYTES + sizeof(PersistBars) + 1024;
 }
 
 // weight-resident when the [128 x K] block plus a >= 3-deep A ring fits; otherwise stream both operands
-inline PersistCfg persist_config(int K, int n_tiles_n, bool resid, bool allow_bres) {
+inline PersistCfg persist_config(int K, int n_tiles_n, bool resid, bool one_group_only) {
   static const bool no_bres = [] {
     const char* e = getenv("KDB200_GEMM_NO_BRES");
     return e != nullptr && e[0] == '1';
   }();
+  static const int max_nb = [] {
+    const char* e = getenv("KDB200_GEMM_MAX_NB");
+    return e != nullptr && e[0] >= '1' && e[0] <= '4' ? e[0] - '0' : 3;
+  }();
   const int nkb = K / BK;
-  if (allow_bres && !no_bres && nkb <= 6 && n_tiles_n <= num_sms()) {
-    for (int st = 6; st >= 3; --st) {
-      PersistCfg c{st, 1, 2};
-      if (persist_smem(nkb, resid, c) <= P_SMEM_LIMIT) return c;
+  if (!no_bres && n_tiles_n <= num_sms()) {
+    // several resident n-blocks: the A ring must hold two whole A tiles so the next m-tile streams in behind the current one
+    for (int nb = max_nb; nb >= 2; --nb) {
+      if (n_tiles_n % nb != 0 || (one_group_only && nb != n_tiles_n)) continue;
+      for (int st = 3 * nkb; st >= 2 * nkb; st -= nkb) {
+        PersistCfg c{st, 1, 2, nb};
+        if (st <= P_MAX_STAGES && persist_smem(nkb, resid, c) <= P_SMEM_LIMIT) return c;
+      }
+    }
+    if (nkb <= 6 && !(one_group_only && n_tiles_n != 1)) {
+      for (int st = 6; st >= 3; --st) {
+        PersistCfg c{st, 1, 2, 1};
+        if (persist_smem(nkb, resid, c) <= P_SMEM_LIMIT) return c;
+      }
     }
   }
-  PersistCfg c{resid ? 3 : 4, 0, 2};
+  PersistCfg c{4, 0, 2, 1};
   return c;
 }
 
@@ -413,7 +508,8 @@ int launch_persist(const bf16* A, const bf16* W, TcParams p, cudaStream_t st) {
     }
   }
   const int n_tiles_n = p.N / P_BN;
-  const PersistCfg cfg = persist_config(p.K, n_tiles_n, EPI == TCE_RESID || EPI == TCE_SPLIT, EPI != TCE_QKV);   // q/k tiles are heavier than v tiles: keep the dynamic order
+  // QKV: q/k tiles are heavier than v tiles, so a CTA must either own all n-blocks (resident) or take tiles in the mixed streaming order
+  const PersistCfg cfg = persist_config(p.K, n_tiles_n, EPI == TCE_RESID || EPI == TCE_SPLIT, EPI == TCE_QKV);
   p.stages = cfg.stages;
   const size_t smem = persist_smem(p.K / BK, EPI == TCE_RESID || EPI == TCE_SPLIT, cfg);
   static bool attr_set = false;
@@ -421,9 +517,10 @@ int launch_persist(const bf16* A, const bf16* W, TcParams p, cudaStream_t st) {
     KDB_CUDA(cudaFuncSetAttribute(gemm_tc_persist<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM_LIMIT));
     attr_set = true;
   }
-  const int64_t tiles = (int64_t)n_tiles_n * ceil_div(p.M, BM);
+  const int n_groups = cfg.b_res ? n_tiles_n / cfg.nb : n_tiles_n;
+  const int64_t tiles = cfg.b_res ? (int64_t)n_groups * ceil_div(p.M, BM) : (int64_t)n_tiles_n * ceil_div(p.M, BM);
   int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  if (cfg.b_res && tiles > n_tiles_n) grid = grid / n_tiles_n * n_tiles_n;      // keep every CTA on one n-block
+  if (cfg.b_res) grid = grid / n_groups * n_groups;      // every CTA stays on one group of n-blocks
   static const bool trace_on = [] {
     const char* e = getenv("KDB200_GEMM_TRACE");
     return e != nullptr && e[0] == '1';
@@ -440,14 +537,14 @@ int launch_persist(const bf16* A, const bf16* W, TcParams p, cudaStream_t st) {
     static long long h[32 * 16];
     KDB_CUDA(cudaMemcpyAsync(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost, st));
     KDB_CUDA(cudaStreamSynchronize(st));
-    const char* names[13] = {"prod_issued", "mma_pre_empty", "mma_post_empty", "mma_committed", "epi_top", "epi_store_drained", "epi_bar1",
-                             "epi_tmem_full", "epi_pass0", "epi_pass1", "epi_sts_done", "epi_bar2", "epi_store_issued"};
-    fprintf(stderr, "GEMM trace EPI=%d M=%lld N=%d K=%d grid=%d stages=%d b_res=%d (cycles relative to tile 0 mma_pre_empty)\n", EPI, (long long)p.M,
-            p.N, p.K, grid, cfg.stages, cfg.b_res);
+    const char* names[16] = {"prod_issued", "mma_pre_empty", "mma_post_empty", "mma_committed", "epi_top", "epi_store_drained", "epi_bar1",
+                             "epi_tmem_full", "epi_pass0", "epi_pass1", "epi_sts_done", "epi_bar2", "epi_store_issued", "mma_full0", "mma_issued0", "mma_full1"};
+    fprintf(stderr, "GEMM trace EPI=%d M=%lld N=%d K=%d grid=%d stages=%d b_res=%d nb=%d (cycles relative to tile 0 mma_pre_empty)\n", EPI, (long long)p.M,
+            p.N, p.K, grid, cfg.stages, cfg.b_res, cfg.nb);
     const long long t0 = h[1];
     for (int t = 0; t < 12; ++t) {
       fprintf(stderr, " tile %2d:", t);
-      for (int k = 0; k < 13; ++k) fprintf(stderr, " %s=%lld", names[k], h[t * 16 + k] ? h[t * 16 + k] - t0 : -1);
+      for (int k = 0; k < 16; ++k) fprintf(stderr, " %s=%lld", names[k], h[t * 16 + k] ? h[t * 16 + k] - t0 : -1);
       fprintf(stderr, "\n");
     }
   }

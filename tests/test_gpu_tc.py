@@ -7,7 +7,9 @@ DEV = "cuda"
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 128), (128, 64, 64), (256, 384, 128), (8192, 768, 128), (1000, 256, 512),
-                                   (2048, 512, 1536), (196, 768, 256), (4096, 1024, 2048), (32768, 128, 384)])
+                                   (2048, 512, 1536), (196, 768, 256), (4096, 1024, 2048), (32768, 128, 384),
+                                   # K = 128 with several n-blocks: the weight-resident kernel keeps 2-3 n-blocks and loads each A tile once
+                                   (65536, 768, 128), (40000, 384, 128), (20000, 256, 128), (300, 768, 128), (33000, 512, 128)])
 def test_gemm_bf16_tcgen05(M, N, K):
     from k_diffusion import _native as N_
     g = torch.Generator(device=DEV).manual_seed(M + N + K)
