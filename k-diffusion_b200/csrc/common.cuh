@@ -72,3 +72,9 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 constexpr int kNumSMs = 148;
 
 }  // namespace kdb
+
+// Programmatic dependent launch: let the CTAs of the next kernel in the stream (if it was launched with the programmatic
+// attribute -- the persistent GEMM is) be scheduled as soon as every CTA of this grid has passed this point or exited.
+// The caller must itself be past any dependency on ITS predecessor, i.e. ordinary (fully serialised) launches call it first thing.
+#define KDB_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+

@@ -105,6 +105,7 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const T* __restrict__ x, T
 template <int G, int CH>
 __global__ void __launch_bounds__(256) rmsnorm_bf16_vec_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const float* __restrict__ scale,
                                                                int64_t scale_bstride, int64_t rows_per_batch, int64_t rows) {
+  KDB_PDL_TRIGGER();
   constexpr int C = G * CH * 8;
   constexpr int ROWS_PER_WARP = 32 / G;
   const int lane = threadIdx.x & 31;
@@ -378,17 +379,23 @@ int launch_qknorm_rope(T* qkv, const float* pos, const float* freqs, const float
 template int launch_qknorm_rope<float>(float*, const float*, const float*, const float*, int64_t, int, int, int, cudaStream_t);
 template int launch_qknorm_rope<bf16>(bf16*, const float*, const float*, const float*, int64_t, int, int, int, cudaStream_t);
 
+// RoPE table for the QKV epilogue: float4 [(head * nf + i) * T + token] = (cos t_2i, cos t_2i+1, sin t_2i, sin t_2i+1), i < nf.
+// Token-minor, so the 32 threads of an epilogue warp (32 consecutive tokens) read 512 contiguous bytes per load, and the
+// (cos, cos, sin, sin) order is what the packed-fp32 rotation consumes.  theta_j = pos_h * f_j (j < nf) or pos_w * f_{j-nf}.
 __global__ void __launch_bounds__(256) rope_table_kernel(const float* __restrict__ pos, const float* __restrict__ freqs,
                                                          float2* __restrict__ out, int T_tokens, int nh, int nf) {
   const int total = T_tokens * nh * 2 * nf;
+  float* o = reinterpret_cast<float*>(out);
   for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
-    const int j = i % (2 * nf);
-    const int h = (i / (2 * nf)) % nh;
-    const int t = i / (2 * nf * nh);
+    const int t = i % T_tokens;
+    const int j = (i / T_tokens) % (2 * nf);
+    const int h = i / (T_tokens * 2 * nf);
     const float theta = (j < nf ? pos[t * 2] : pos[t * 2 + 1]) * freqs[h * nf + (j < nf ? j : j - nf)];
     float s, c;
     sincosf(theta, &s, &c);
-    out[i] = make_float2(c, s);
+    const int64_t base = (((int64_t)h * nf + (j >> 1)) * T_tokens + t) * 4;
+    o[base + (j & 1)] = c;
+    o[base + 2 + (j & 1)] = s;
   }
 }
 

@@ -14,7 +14,7 @@ struct GemmEpi {
   const float* fac = nullptr;    // EPI_SPLIT_LERP: device scalar (TokenSplit.fac)
   int hc = 0, wc = 0, C = 0;     // EPI_SPLIT_LERP: coarse grid and fine channel count (N == 4*C)
   // EPI_QKV_ROPE (tensor-core path only): cosine-sim scaling + axial RoPE of the q and k thirds (N == 3*C, d_head 64)
-  const float2* rope = nullptr;  // [T_tokens, nh, 16] (cos, sin) of theta
+  const float2* rope = nullptr;  // launch_rope_table: float4 [nh][8][T_tokens] = (cos, cos, sin, sin) of the angle pairs
   const float* qk_scale = nullptr;   // [nh]
   int nh = 0, T_tokens = 0;
   // TokenMerge folded into the A-operand load (tensor-core path only): A = fine tokens [B, 2*mhc, 2*mwc, mC], K = 4*mC in

@@ -53,6 +53,7 @@ template <> __device__ __forceinline__ void store8<bf16>(bf16* o, const float (&
 template <typename T, int PH, int PW, int TT>
 __global__ void __launch_bounds__(256) patch_in_tiled(const float* __restrict__ x, const float* __restrict__ sigma, float sd,
                                                       const float* __restrict__ W, T* __restrict__ out, PatchGeom g) {
+  KDB_PDL_TRIGGER();
   extern __shared__ __align__(16) float sm[];
   constexpr int N = TT * 32;
   const int K = PH * PW * g.C;

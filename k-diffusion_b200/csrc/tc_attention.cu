@@ -51,6 +51,7 @@ __device__ __forceinline__ uint32_t p_offset(int row, int chunk16) {   // byte o
 template <int MODE>
 __global__ void __launch_bounds__(160, MODE == MODE_WINDOW ? 4 : 2) attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_kv,
                                                                                       const AttnParams p) {
+  KDB_PDL_TRIGGER();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = base;

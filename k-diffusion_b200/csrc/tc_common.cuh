@@ -12,6 +12,14 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the stream is
+// still running; pdl_wait() blocks until the predecessor has completed and its writes are visible.  pdl_launch_dependents()
+// tells the scheduler that the NEXT kernel's CTAs may be placed as soon as this grid's CTAs have all passed this point (or
+// exited) and resources free up.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -172,6 +180,36 @@ __device__ __forceinline__ float tanh_approx(float x) {
 __device__ __forceinline__ float gelu_fast(float x) {
   const float u = x * fmaf(0.0356774081f, x * x, 0.7978845608f);     // sqrt(2/pi) (x + 0.044715 x^3)
   return x * fmaf(0.5f, tanh_approx(u), 0.5f);
+}
+
+// ---------------------------------------------------------------- packed fp32 (sm_100 FFMA2 / FMUL2: two lanes per issue slot)
+// The GEMM epilogues are bound by instruction issue, not by the fp32 datapath: pairing neighbouring columns halves the
+// number of multiply / fma instructions.  Results are bit-identical to the scalar .rn operations.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+// value * gelu_fast(gate) for two (value, gate) pairs
+__device__ __forceinline__ f32x2 geglu2(f32x2 val, f32x2 gate) {
+  const f32x2 c1 = pk2(0.0356774081f, 0.0356774081f), c0 = pk2(0.7978845608f, 0.7978845608f), half = pk2(0.5f, 0.5f);
+  const f32x2 u = mul2(gate, fma2(c1, mul2(gate, gate), c0));
+  float u0, u1;
+  upk2(u, u0, u1);
+  const f32x2 t = pk2(tanh_approx(u0), tanh_approx(u1));
+  return mul2(val, mul2(gate, fma2(half, t, half)));
 }
 
 // ---------------------------------------------------------------- descriptors

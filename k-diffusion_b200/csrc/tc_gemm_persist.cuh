@@ -28,7 +28,7 @@ constexpr size_t P_SMEM_LIMIT = 227 * 1024;
 struct PersistBars {
   uint64_t full[P_MAX_STAGES], empty[P_MAX_STAGES];
   uint64_t tmem_full[2], tmem_empty[2];
-  uint64_t resid_full[2], b_full;   // resid_full per epilogue group: a waiter must observe every phase of its barrier
+  uint64_t resid_full[2][2], b_full;   // resid_full[group][buffer]: a waiter must observe every phase of its barrier
   uint32_t tmem;
 };
 
@@ -106,25 +106,28 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
       tc::mbar_init(&bars->tmem_full[a], 1);
       tc::mbar_init(&bars->tmem_empty[a], 128);          // one ping-pong epilogue group (4 warps)
     }
-    tc::mbar_init(&bars->resid_full[0], 1);
-    tc::mbar_init(&bars->resid_full[1], 1);
+    for (int a = 0; a < 4; ++a) tc::mbar_init(&bars->resid_full[a >> 1][a & 1], 1);
     tc::mbar_init(&bars->b_full, 1);
     tc::fence_barrier_init();
+    // The resident weight block does not depend on the previous kernel: it is requested before the programmatic-launch wait
+    // below, so (with the prologue) it overlaps the tail of the predecessor.
+    if (cfg.b_res && n_local > 0) {
+      tc::mbar_arrive_expect_tx(&bars->b_full, (uint32_t)(nb * nkb) * P_B_TILE_BYTES);
+      for (int j = 0; j < nb; ++j)
+        for (int kb = 0; kb < nkb; ++kb)
+          tc::tma_load_2d(sB + (size_t)(j * nkb + kb) * P_B_TILE_BYTES, &tmb, &bars->b_full, kb * BK, (ng * nb + j) * P_BN);
+    }
   }
   if (warp == 1) tc::tmem_alloc(&bars->tmem, 2 * P_BN);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = bars->tmem;
+  tc::pdl_wait();                    // everything below reads or writes tensors the previous kernel may still be producing
+  tc::pdl_launch_dependents();
 
   if (warp == 0) {
     if (tc::elect_one()) {
-      if (cfg.b_res && n_local > 0) {       // this CTA's n-blocks never change
-        tc::mbar_arrive_expect_tx(&bars->b_full, (uint32_t)(nb * nkb) * P_B_TILE_BYTES);
-        for (int j = 0; j < nb; ++j)
-          for (int kb = 0; kb < nkb; ++kb)
-            tc::tma_load_2d(sB + (size_t)(j * nkb + kb) * P_B_TILE_BYTES, &tmb, &bars->b_full, kb * BK, (ng * nb + j) * P_BN);
-      }
       uint32_t s = 0, ph = 0;      // ring slot / phase (carried incrementally: no division in the loop)
       int jj = 0;
       for (uint32_t it = 0; it < (uint32_t)n_local; ++it) {
@@ -175,16 +178,12 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
         const uint32_t d = tmem + acc * P_BN;
         const bool first = j == 0, last = j + 1 == (uint32_t)nb;
         uint32_t ss = s0, pp = ph0, aa = a0, bb = bres ? bj : a0 + A_STAGE_BYTES;
-        for (int kb = 0; kb < nkb; ++kb) {
-          if (first) {                                              // first use of this A k-block
-            tc::mbar_wait(&bars->full[ss], pp);
-            tc::tc_fence_after();
-          }
-          const uint64_t adesc = tc::smem_desc_k_sw128(aa);
-          const uint64_t bdesc = tc::smem_desc_k_sw128(bb);
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) tc::umma_bf16(d, adesc + 2ull * k, bdesc + 2ull * k, IDESC, (uint32_t)((kb | k) != 0));
-          if (last) tc::umma_commit(&bars->empty[ss]);              // last n-block of this m-tile: the stage may be refilled
+        // k-blocks go in pairs: both waits and all descriptor arithmetic first, then eight tcgen05.mma back to back (the tensor
+        // pipe would otherwise idle while this rarely-scheduled thread works through the loop overhead between two k-blocks).
+        for (int kb = 0; kb < nkb; kb += 2) {
+          const bool two = kb + 1 < nkb;
+          const uint32_t sa = ss, aa0 = aa, bb0 = bb;
+          if (first) tc::mbar_wait(&bars->full[sa], pp);
           aa += sbytes;
           bb += bres ? (uint32_t)P_B_TILE_BYTES : sbytes;
           if (++ss == n_stages) {
@@ -192,6 +191,36 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
             pp ^= 1u;
             aa = stage_base;
             if (!bres) bb = stage_base + A_STAGE_BYTES;
+          }
+          const uint32_t sb = ss, aa1 = aa, bb1 = bb;
+          if (two) {
+            if (first) tc::mbar_wait(&bars->full[sb], pp);
+            aa += sbytes;
+            bb += bres ? (uint32_t)P_B_TILE_BYTES : sbytes;
+            if (++ss == n_stages) {
+              ss = 0;
+              pp ^= 1u;
+              aa = stage_base;
+              if (!bres) bb = stage_base + A_STAGE_BYTES;
+            }
+          }
+          if (first) tc::tc_fence_after();
+          const uint64_t ad0 = tc::smem_desc_k_sw128(aa0), bd0 = tc::smem_desc_k_sw128(bb0);
+          const uint64_t ad1 = tc::smem_desc_k_sw128(aa1), bd1 = tc::smem_desc_k_sw128(bb1);
+          const uint32_t acc0 = (uint32_t)(kb != 0);
+          tc::umma_bf16(d, ad0, bd0, IDESC, acc0);
+          tc::umma_bf16(d, ad0 + 2ull, bd0 + 2ull, IDESC, 1u);
+          tc::umma_bf16(d, ad0 + 4ull, bd0 + 4ull, IDESC, 1u);
+          tc::umma_bf16(d, ad0 + 6ull, bd0 + 6ull, IDESC, 1u);
+          if (two) {
+            tc::umma_bf16(d, ad1, bd1, IDESC, 1u);
+            tc::umma_bf16(d, ad1 + 2ull, bd1 + 2ull, IDESC, 1u);
+            tc::umma_bf16(d, ad1 + 4ull, bd1 + 4ull, IDESC, 1u);
+            tc::umma_bf16(d, ad1 + 6ull, bd1 + 6ull, IDESC, 1u);
+          }
+          if (last) {                                               // last n-block of this m-tile: the stages may be refilled
+            tc::umma_commit(&bars->empty[sa]);
+            if (two) tc::umma_commit(&bars->empty[sb]);
           }
         }
         tc::umma_commit(&bars->tmem_full[acc]);
@@ -219,7 +248,11 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
     const int q = warp & 3;                  // TMEM lane quadrant this warp may touch
     const int row = q * 32 + lane;
     const bool issuer = (ew & 3) == 0 && lane == 0;
-    uint8_t* ct = sC + (size_t)grp * P_OUT_BYTES;
+    // staging tiles: one per group, or two per group (sc_bufs == 4, residual variants when shared memory allows): the residual of
+    // the group's NEXT tile is then loaded into the other buffer a whole tile period ahead instead of behind the current store
+    const uint32_t nbuf = (uint32_t)cfg.sc_bufs >> 1;
+    uint8_t* const ct_base = sC + (size_t)grp * nbuf * P_OUT_BYTES;
+    uint8_t* ct = ct_base;
     float facv = 0.f;
     if constexpr (EPI == TCE_SPLIT) facv = __ldg(p.fac);
     // residual / skip tile of `tile` -> this group's staging tile (issuer thread only; the staging tile must be free)
@@ -227,7 +260,9 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
       if constexpr (RES) {
         int m0, n0, j_;
         coords(it_, m0, n0, j_);
-        uint64_t* rf = &bars->resid_full[grp];
+        const uint32_t b_ = nbuf == 2 ? (it_ >> 1) & 1u : 0u;
+        uint64_t* rf = &bars->resid_full[grp][b_];
+        uint8_t* ct = ct_base + (size_t)b_ * P_OUT_BYTES;
         tc::mbar_arrive_expect_tx(rf, P_OUT_BYTES);
         if constexpr (EPI == TCE_SPLIT) {   // skip tensor: fine tokens of quadrant (nh, nw) = n0 / Cf, channels e0..e0+127
           const int qd = n0 / p.Cf, e0 = n0 - qd * p.Cf;
@@ -242,10 +277,20 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
     };
     if constexpr (RES) {
       if (issuer && grp < n_local) load_resid((uint32_t)grp);
+      if (issuer && nbuf == 2 && grp + 2 < n_local) load_resid((uint32_t)grp + 2);
     }
     for (uint32_t it = (uint32_t)grp; it < (uint32_t)n_local; it += 2) {
       int m0, n0, j_;
       coords(it, m0, n0, j_);
+      const uint32_t buf = nbuf == 2 ? (it >> 1) & 1u : 0u;
+      ct = ct_base + (size_t)buf * P_OUT_BYTES;
+      if constexpr (RES) {
+        // two buffers: the store of this group's previous tile (other buffer) drained long ago -> refill it for the tile after this one
+        if (nbuf == 2 && issuer && it >= 2 + (uint32_t)grp && it + 2 < (uint32_t)n_local) {
+          tc::tma_store_wait_read();
+          load_resid(it + 2);
+        }
+      }
       const int64_t m = (int64_t)m0 + row;
       const uint32_t acc = (uint32_t)grp, use = it >> 1;
       // fused RMSNorm (consumer side): the producer of x left sum(x^2) of every token, one slot per 128 channels
@@ -260,33 +305,37 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
         if (parts > 4) ssum += (s1.x + s1.y) + (s1.z + s1.w);
         rstd = rsqrtf(ssum / (float)p.K + 1e-6f);
       }
-      // QKV: the RoPE table row does not depend on the accumulator -> fetch it before waiting for the MMA
-      float4 cs[2][8];
-      if constexpr (EPI == TCE_QKV) {
-        const int64_t tok = (m < p.M ? m : 0) % p.T;
+      // QKV: the RoPE table row does not depend on the accumulator -> pass 0's row is fetched before waiting for the MMA, pass
+      // 1's while pass 0 is being scaled / packed / stored (one live copy of the row: 32 registers instead of 64)
+      float4 cs[8];
+      [[maybe_unused]] auto load_cs = [&](int g) {
+        const int n = n0 + g * 64;
+        const int t3 = n / p.C, head = (n - t3 * p.C) >> 6;
+        if (t3 < 2) {
+          const int64_t tok = (m < p.M ? m : 0) % p.T;
+          const float4* tb = reinterpret_cast<const float4*>(p.rope) + (int64_t)head * 8 * p.T + tok;   // [head][i][token]
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          const int n = n0 + g * 64;
-          const int t3 = n / p.C, head = (n - t3 * p.C) >> 6;
-          if (t3 < 2) {
-            const float4* tb = reinterpret_cast<const float4*>(p.rope + (tok * p.nh + head) * 16);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) cs[g][i] = __ldg(tb + i);
-          }
+          for (int i = 0; i < 8; ++i) cs[i] = __ldg(tb + (int64_t)i * p.T);
         }
-      }
+      };
+      if constexpr (EPI == TCE_QKV) load_cs(0);
       if (issuer) KDB_TRACE(4);
-      if constexpr (!RES) {   // (RES: the residual load into the staging tile was issued after that wait; resid_full orders the writes)
-        if (issuer) tc::tma_store_wait_read();             // this group's previous store has finished READING the staging tile
-        if (issuer) KDB_TRACE(5);
-        tc::named_barrier_sync(1 + 2 * grp, 128);
-      }
+      // The staging tile is needed only at the first shared-memory store of pass 0: waiting for the previous TMA store to
+      // drain is deferred until then (staging_free below), behind the accumulator wait and pass 0's arithmetic.
+      // (RES: the residual load into the staging tile was issued after that drain; resid_full orders the writes.)
+      auto staging_free = [&]() {
+        if constexpr (!RES) {
+          if (issuer) tc::tma_store_wait_read();           // this group's previous store has finished READING the staging tile
+          if (issuer) KDB_TRACE(5);
+          tc::named_barrier_sync(1 + 2 * grp, 128);
+        }
+      };
       if (issuer) KDB_TRACE(6);
       tc::mbar_wait(&bars->tmem_full[acc], use & 1u);
       tc::tc_fence_after();
       if (issuer) KDB_TRACE(7);
       float ss_acc[4] = {0.f, 0.f, 0.f, 0.f};   // producer side: sum of squares of the row this thread writes
-      if constexpr (RES) tc::mbar_wait(&bars->resid_full[grp], use & 1u);
+      if constexpr (RES) tc::mbar_wait(&bars->resid_full[grp][buf], (nbuf == 2 ? use >> 1 : use) & 1u);
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
         float v[64];
@@ -304,7 +353,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
           tc::mbar_arrive(&bars->tmem_empty[acc]);
         }
         if (issuer) KDB_TRACE(8 + g);
-        if (p.ss_in != nullptr) {
+        if (EPI != TCE_GEGLU && p.ss_in != nullptr) {
           // fused RMSNorm row scale.  q and k are cosine-normalised afterwards (scale invariant): only v needs it.
           bool apply = true;
           if constexpr (EPI == TCE_QKV) apply = (n0 + g * 64) >= 2 * p.C;
@@ -316,14 +365,29 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
         // Epilogue arithmetic stays in fp32 and is rounded to bf16 once, at the pack (a K=128 tile leaves ~4 ALU
         // instructions per output element before the epilogue, not the tensor pipe, sets the pace).
         if constexpr (EPI == TCE_GEGLU) {
+          // columns come as [8 value | 8 gate] groups (interleaved up_proj rows); packed fp32 pairs halve the issue count
+          const tc::f32x2 r2 = tc::pk2(rstd, rstd);
+          uint4 og[4];
 #pragma unroll
           for (int gg = 0; gg < 4; ++gg) {
-            float o[8];
+            uint32_t o[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = v[gg * 16 + j] * tc::gelu_fast(v[gg * 16 + 8 + j]);
-            *reinterpret_cast<uint4*>(ct + tc::sw128_offset(row, g * 4 + gg)) =
-                make_uint4(tc::pack_bf16x2(o[0], o[1]), tc::pack_bf16x2(o[2], o[3]), tc::pack_bf16x2(o[4], o[5]), tc::pack_bf16x2(o[6], o[7]));
+            for (int j = 0; j < 4; ++j) {
+              tc::f32x2 val = tc::pk2(v[gg * 16 + 2 * j], v[gg * 16 + 2 * j + 1]);
+              tc::f32x2 gate = tc::pk2(v[gg * 16 + 8 + 2 * j], v[gg * 16 + 8 + 2 * j + 1]);
+              if (p.ss_in != nullptr) {
+                val = tc::mul2(val, r2);
+                gate = tc::mul2(gate, r2);
+              }
+              float o0, o1;
+              tc::upk2(tc::geglu2(val, gate), o0, o1);
+              o[j] = tc::pack_bf16x2(o0, o1);
+            }
+            og[gg] = make_uint4(o[0], o[1], o[2], o[3]);
           }
+          if (g == 0) staging_free();
+#pragma unroll
+          for (int gg = 0; gg < 4; ++gg) *reinterpret_cast<uint4*>(ct + tc::sw128_offset(row, g * 4 + gg)) = og[gg];
         } else {
           if constexpr (RES) {
             const uint8_t* rt = ct + g * SUB_TILE_BYTES;     // this thread reads and then overwrites only its own row
@@ -360,29 +424,45 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
             const int n = n0 + g * 64;               // one head of q, k or v (feature order (t nh e), d_head 64)
             const int t3 = n / p.C, head = (n - t3 * p.C) >> 6;
             if (t3 < 2) {
-              float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+              // cosine-sim scale + axial RoPE on packed fp32 pairs.  Columns (2i, 2i+1) pair with (16+2i, 17+2i); the table
+              // holds (cos_2i, cos_2i+1, sin_2i, sin_2i+1) per float4, so every operand is a natural register pair.
+              tc::f32x2 P[32];
 #pragma unroll
-              for (int i = 0; i < 64; i += 4) {
-                s0 = fmaf(v[i], v[i], s0);
-                s1 = fmaf(v[i + 1], v[i + 1], s1);
-                s2 = fmaf(v[i + 2], v[i + 2], s2);
-                s3 = fmaf(v[i + 3], v[i + 3], s3);
+              for (int i = 0; i < 32; ++i) P[i] = tc::pk2(v[2 * i], v[2 * i + 1]);
+              tc::f32x2 q0 = tc::mul2(P[0], P[0]), q1 = tc::mul2(P[1], P[1]), q2 = tc::mul2(P[2], P[2]), q3 = tc::mul2(P[3], P[3]);
+#pragma unroll
+              for (int i = 4; i < 32; i += 4) {
+                q0 = tc::fma2(P[i], P[i], q0);
+                q1 = tc::fma2(P[i + 1], P[i + 1], q1);
+                q2 = tc::fma2(P[i + 2], P[i + 2], q2);
+                q3 = tc::fma2(P[i + 3], P[i + 3], q3);
               }
-              const float sc = sqrtf(__ldg(p.qk_scale + head)) * rsqrtf((s0 + s1) + (s2 + s3) + 1e-6f);
+              float e0, e1, e2, e3, e4, e5, e6, e7;
+              tc::upk2(q0, e0, e1);
+              tc::upk2(q1, e2, e3);
+              tc::upk2(q2, e4, e5);
+              tc::upk2(q3, e6, e7);
+              const float sc = sqrtf(__ldg(p.qk_scale + head)) * rsqrtf(((e0 + e1) + (e2 + e3)) + ((e4 + e5) + (e6 + e7)) + 1e-6f);
+              const tc::f32x2 sc2 = tc::pk2(sc, sc);
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const float4 c4 = cs[g][i];
-                const float x1a = v[2 * i] * sc, x2a = v[16 + 2 * i] * sc, x1b = v[2 * i + 1] * sc, x2b = v[17 + 2 * i] * sc;
-                v[2 * i] = x1a * c4.x - x2a * c4.y;
-                v[16 + 2 * i] = x2a * c4.x + x1a * c4.y;
-                v[2 * i + 1] = x1b * c4.z - x2b * c4.w;
-                v[17 + 2 * i] = x2b * c4.z + x1b * c4.w;
+                const tc::f32x2 C = tc::pk2(cs[i].x, cs[i].y), S = tc::pk2(cs[i].z, cs[i].w);
+                const tc::f32x2 NS = S ^ 0x8000000080000000ull;
+                const tc::f32x2 X1 = P[i], X2 = P[8 + i];
+                P[i] = tc::mul2(tc::fma2(X2, NS, tc::mul2(X1, C)), sc2);
+                P[8 + i] = tc::mul2(tc::fma2(X1, S, tc::mul2(X2, C)), sc2);
               }
+              if (g == 0) load_cs(1);                // the table row of pass 1 streams in behind the rest of pass 0
 #pragma unroll
-              for (int i = 32; i < 64; ++i) v[i] *= sc;
+              for (int i = 16; i < 32; ++i) P[i] = tc::mul2(P[i], sc2);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) tc::upk2(P[i], v[2 * i], v[2 * i + 1]);
+            } else if (g == 0) {
+              load_cs(1);
             }
           }
           uint8_t* cg = ct + g * SUB_TILE_BYTES;
+          if (g == 0) staging_free();
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             *reinterpret_cast<uint4*>(cg + tc::sw128_offset(row, j)) =
@@ -422,7 +502,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
         tc::tma_store_commit();
         KDB_TRACE(12);
         if constexpr (RES) {   // prefetch the residual of this group's next tile as soon as the store has drained the staging tile
-          if (it + 2 < (uint32_t)n_local) {
+          if (nbuf == 1 && it + 2 < (uint32_t)n_local) {
             tc::tma_store_wait_read();
             load_resid(it + 2);
           }
@@ -475,6 +555,12 @@ inline PersistCfg persist_config(int K, int n_tiles_n, bool resid, bool one_grou
       }
     }
     if (nkb <= 6 && !(one_group_only && n_tiles_n != 1)) {
+      if (resid) {   // two staging tiles per epilogue group hide the residual-load latency; worth two ring stages
+        for (int st = 6; st >= 4; --st) {
+          PersistCfg c{st, 1, 4, 1};
+          if (st >= 2 * nkb && persist_smem(nkb, resid, c) <= P_SMEM_LIMIT) return c;
+        }
+      }
       for (int st = 6; st >= 3; --st) {
         PersistCfg c{st, 1, 2, 1};
         if (persist_smem(nkb, resid, c) <= P_SMEM_LIMIT) return c;
@@ -531,7 +617,21 @@ int launch_persist(const bf16* A, const bf16* W, TcParams p, cudaStream_t st) {
     KDB_CUDA(cudaMemsetAsync(trace_buf, 0, 32 * 16 * sizeof(long long), st));
     p.trace = trace_buf;
   }
-  gemm_tc_persist<EPI><<<grid, P_THREADS, smem, st>>>(ta, tb, tcm, tr, p, cfg);
+  static const bool no_pdl = [] {
+    const char* e = getenv("KDB200_NO_PDL");
+    return e != nullptr && e[0] == '1';
+  }();
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = dim3((unsigned)grid);
+  lc.blockDim = dim3(P_THREADS);
+  lc.dynamicSmemBytes = smem;
+  lc.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = attr;
+  lc.numAttrs = no_pdl || trace_on ? 0 : 1;
+  KDB_CUDA(cudaLaunchKernelEx(&lc, gemm_tc_persist<EPI>, ta, tb, tcm, tr, p, cfg));
   KDB_LAUNCH_CHECK(F_GEMM_TC, st);
   if (trace_on) {
     static long long h[32 * 16];

@@ -73,7 +73,7 @@ struct TcParams {
   int N, K, stages;
   int hc, wc, Cf;
   // QKV
-  const float2* rope;    // [T, nh, 16]
+  const float2* rope;    // float4 [nh][8][T] (cos, cos, sin, sin) of angle pairs, see rope_table_kernel
   const float* qk_scale; // [nh]
   int C, nh, T;
   // PATCHOUT (4x4 patches, 3 output channels): un-patch to NCHW fp32 + Karras combine with the input latent
@@ -138,6 +138,7 @@ template <int BN, int EPI>
 __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUtensorMap tmb,
                                                       const __grid_constant__ CUtensorMap tmc, const __grid_constant__ CUtensorMap tmr,
                                                       const TcParams p) {
+  KDB_PDL_TRIGGER();
   extern __shared__ uint8_t smem_raw[];
   constexpr int B_STAGE_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
@@ -350,15 +351,15 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
 #pragma unroll
               for (int i = 0; i < 64; ++i) v[i] = bf16_round(v[i] * sc);
               const int64_t tok = (m < p.M ? m : 0) % p.T;
-              const float4* tb = reinterpret_cast<const float4*>(p.rope + (tok * p.nh + head) * 16);
+              const float4* tb = reinterpret_cast<const float4*>(p.rope) + (int64_t)head * 8 * p.T + tok;   // [head][i][token]
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const float4 cs = __ldg(tb + i);      // (cos, sin) of theta_{2i}, theta_{2i+1}
+                const float4 cs = __ldg(tb + (int64_t)i * p.T);      // (cos t_2i, cos t_2i+1, sin t_2i, sin t_2i+1)
                 const float x1a = v[2 * i], x2a = v[16 + 2 * i], x1b = v[2 * i + 1], x2b = v[17 + 2 * i];
-                v[2 * i] = x1a * cs.x - x2a * cs.y;
-                v[16 + 2 * i] = x2a * cs.x + x1a * cs.y;
-                v[2 * i + 1] = x1b * cs.z - x2b * cs.w;
-                v[17 + 2 * i] = x2b * cs.z + x1b * cs.w;
+                v[2 * i] = x1a * cs.x - x2a * cs.z;
+                v[16 + 2 * i] = x2a * cs.x + x1a * cs.z;
+                v[2 * i + 1] = x1b * cs.y - x2b * cs.w;
+                v[17 + 2 * i] = x2b * cs.y + x1b * cs.w;
               }
             }
           }
@@ -568,6 +569,7 @@ bool tc_gemm_geglu_supported(int64_t M, int N2, int K, bool fused_norm) {
 }
 
 __global__ void __launch_bounds__(256) fold_norm_weights_kernel(const FoldDesc* __restrict__ descs, const float* __restrict__ cond) {
+  KDB_PDL_TRIGGER();
   const FoldDesc d = descs[blockIdx.y];
   const int64_t chunks = (int64_t)d.rows * d.K / 8;
   const float* g = cond + d.ada_off;
