@@ -448,7 +448,10 @@ int forward_impl(KdbModel* m, int B, int H, int W, const float* x, const float* 
     me.mhc = h / 2;
     me.mwc = w / 2;
     const int64_t Mc = (int64_t)B * (h / 2) * (w / 2);
+    bool merge_ss = false;
     if (std::is_same<T, bf16>::value && tc_gemm_supported(Mc, c.width[l + 1], 4 * c.width[l], me)) {
+      merge_ss = m->fuse_norm && c.width[l + 1] % 128 == 0 && tc_gemm_emits_rowss(Mc, c.width[l + 1], 4 * c.width[l], me);
+      if (merge_ss) me.ss_out = ws.rowss;      // row statistics of the merged tokens for the next level's first fused RMSNorm
       if ((rc = launch_gemm_tc(reinterpret_cast<const bf16*>(cur), m->merge_wb[l], reinterpret_cast<bf16*>(nxt), Mc, c.width[l + 1], 4 * c.width[l],
                                me, st)))
         return rc;
@@ -457,7 +460,7 @@ int forward_impl(KdbModel* m, int B, int H, int W, const float* x, const float* 
       if ((rc = launch_merge_gather<T>(cur, mg, B, h, w, c.width[l], st))) return rc;
       if ((rc = linear<T>(mg, WSel<T>::merge(m, l), nxt, Mc, c.width[l + 1], 4 * c.width[l], GemmEpi{}, st))) return rc;
     }
-    m->ss_valid = false;
+    m->ss_valid = merge_ss;
     h /= 2;
     w /= 2;
     if ((rc = tap<T>(m, "L" + std::to_string(l) + ".merge", nxt, (int64_t)B * h * w * c.width[l + 1], st))) return rc;

@@ -51,7 +51,6 @@ __device__ __forceinline__ uint32_t p_offset(int row, int chunk16) {   // byte o
 template <int MODE>
 __global__ void __launch_bounds__(160, MODE == MODE_WINDOW ? 4 : 2) attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_kv,
                                                                                       const AttnParams p) {
-  KDB_PDL_TRIGGER();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = base;
@@ -106,6 +105,8 @@ __global__ void __launch_bounds__(160, MODE == MODE_WINDOW ? 4 : 2) attn_tc_kern
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
+  tc::pdl_wait();                              // programmatic launch: the qkv projection before us must be complete from here on
+  tc::pdl_launch_dependents();
   const uint32_t tmem_s = bars->tmem;          // columns [0,128): S
   // O: 64 columns.  WINDOW: P V is only issued after every thread has read S (bar_p), so O re-uses S's first columns.
   const uint32_t tmem_o = bars->tmem + (MODE == MODE_WINDOW ? 0 : 128);
@@ -363,6 +364,26 @@ bool tc_attention_supported(int h, int w, int nh, int e, int attn_type, int attn
   return false;
 }
 
+// programmatic dependent launch: barrier init / TMEM allocation overlap the tail of the qkv projection (KDB200_NO_PDL=1 disables)
+template <int MODE>
+static cudaError_t launch_attn(dim3 grid, size_t smem, cudaStream_t st, const CUtensorMap& tq, const CUtensorMap& tkv, const AttnParams& p) {
+  static const bool no_pdl = [] {
+    const char* e = getenv("KDB200_NO_PDL");
+    return e != nullptr && e[0] == '1';
+  }();
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = grid;
+  lc.blockDim = dim3(160);
+  lc.dynamicSmemBytes = smem;
+  lc.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = attr;
+  lc.numAttrs = no_pdl ? 0 : 1;
+  return cudaLaunchKernelEx(&lc, attn_tc_kernel<MODE>, tq, tkv, p);
+}
+
 int launch_attention_tc(const bf16* qkv, bf16* out, int B, int h, int w, int nh, int e, int attn_type, int attn_param, int shift,
                         cudaStream_t st) {
   KDB_REQUIRE(tc_attention_supported(h, w, nh, e, attn_type, attn_param), KDB_ERR_UNSUPPORTED, "attention_tc: unsupported shape");
@@ -387,7 +408,7 @@ int launch_attention_tc(const bf16* qkv, bf16* out, int B, int h, int w, int nh,
     }
     p.nblk = 1;
     dim3 grid((unsigned)((h / 8) * (w / 8)), (unsigned)(nh / 2), (unsigned)B);
-    attn_tc_kernel<MODE_WINDOW><<<grid, 160, ATTN_SMEM_WINDOW, st>>>(tm, tm, p);
+    KDB_CUDA(launch_attn<MODE_WINDOW>(grid, ATTN_SMEM_WINDOW, st, tm, tm, p));
   } else if (attn_type == KDB_ATTN_NEIGHBORHOOD) {
     static bool attr_n = false;
     CUtensorMap tkv;
@@ -403,7 +424,7 @@ int launch_attention_tc(const bf16* qkv, bf16* out, int B, int h, int w, int nh,
     }
     p.nblk = 3;      // 14 halo rows = 5 + 5 + 4
     dim3 grid((unsigned)((h / NA_QH) * (w / NA_QW)), (unsigned)nh, (unsigned)B);
-    attn_tc_kernel<MODE_NA><<<grid, 160, ATTN_SMEM, st>>>(tm, tkv, p);
+    KDB_CUDA(launch_attn<MODE_NA>(grid, ATTN_SMEM, st, tm, tkv, p));
   } else {
     const uint64_t T = (uint64_t)h * w;
     const uint64_t dims[3] = {F, T, (uint64_t)B};
@@ -417,7 +438,7 @@ int launch_attention_tc(const bf16* qkv, bf16* out, int B, int h, int w, int nh,
     }
     p.nblk = (int)(T / ROWS);
     dim3 grid((unsigned)(T / ROWS), (unsigned)nh, (unsigned)B);
-    attn_tc_kernel<MODE_GLOBAL><<<grid, 160, ATTN_SMEM, st>>>(tm, tm, p);
+    KDB_CUDA(launch_attn<MODE_GLOBAL>(grid, ATTN_SMEM, st, tm, tm, p));
   }
   KDB_LAUNCH_CHECK(F_ATTN_TC, st);
   return 0;

@@ -33,29 +33,32 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// One probe of the phase.  The suspend-time hint lets the hardware park the thread until the phase completes (or the hint
+// expires) instead of returning after ~100 cycles: warps that wait no longer burn issue slots their scheduler's working warps
+// (epilogue arithmetic, the tcgen05.mma issuer) need.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(200000u)
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (reported as a CUDA error) after ~2 s instead of hanging the GPU box.
 __device__ __forceinline__ uint64_t globaltimer_ns() {
   uint64_t t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+// Bounded wait: a protocol bug traps after 2 s with a message instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const uint64_t t0 = globaltimer_ns();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 255u) == 0 && globaltimer_ns() - t0 > 2000000000ull) {
+    if ((++spins & 63u) == 0 && globaltimer_ns() - t0 > 2000000000ull) {
       printf("libkdb200: mbarrier wait timed out (block %d,%d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, parity);
       __trap();
     }

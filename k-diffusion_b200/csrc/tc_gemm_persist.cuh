@@ -160,7 +160,8 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
       // This thread shares its scheduler with two epilogue warps and is rarely the one selected, so every instruction between
       // two tcgen05.mma costs tens of cycles (measured: ~500 cycles per k-block with runtime divisions in the loop, against 256
       // cycles of tensor work).  Ring position, phase and n-block index are therefore carried incrementally -- no division,
-      // no modulo, addresses by addition.
+      // no modulo, addresses by addition.  (A second issuing warp on another scheduler was tried: no gain -- once this loop
+      // is lean the epilogue groups, not the issue rate, set the tile period.)
       if (cfg.b_res && n_local > 0) tc::mbar_wait(&bars->b_full, 0);
       const uint32_t stage_base = tc::smem_u32(sStage), b_base = tc::smem_u32(sB);
       const uint32_t n_stages = (uint32_t)cfg.stages, sbytes = (uint32_t)stage_bytes;
@@ -409,7 +410,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
               }
             }
           }
-          if constexpr (RES) {
+          if constexpr (RES || EPI == TCE_STORE) {
             if (p.ss_out != nullptr) {
 #pragma unroll
               for (int i = 0; i < 64; i += 4) {
@@ -470,7 +471,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persist(const __grid_con
                            tc::pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]), tc::pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]));
         }
       }
-      if constexpr (RES) {
+      if constexpr (RES || EPI == TCE_STORE) {
         if (p.ss_out != nullptr && m < p.M) {     // statistics of the NEW residual stream for the next fused RMSNorm
           const float ssv = (ss_acc[0] + ss_acc[1]) + (ss_acc[2] + ss_acc[3]);
           if constexpr (EPI == TCE_SPLIT) {       // coarse token m, quadrant qd -> fine token

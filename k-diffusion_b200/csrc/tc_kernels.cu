@@ -482,7 +482,7 @@ bool tc_gemm_emits_rowss(int64_t M, int N, int K, const GemmEpi& epi) {
   TcParams p{};
   p.N = N;
   if (!use_persistent(p)) return false;
-  if (epi.mode == EPI_RESID) return N <= 128 * SS_PARTS;
+  if (epi.mode == EPI_RESID || epi.mode == EPI_STORE) return N <= 128 * SS_PARTS;   // (STORE: the TokenMerge projection)
   if (epi.mode == EPI_SPLIT_LERP) {
     int bw, bh;
     return epi.C % P_BN == 0 && epi.C <= 128 * SS_PARTS && M % epi.wc == 0 && quad_box(epi.wc, &bw, &bh);
