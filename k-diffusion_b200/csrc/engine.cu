@@ -58,6 +58,7 @@ struct KdbModel {
   bool ss_valid = false;            // ws.rowss describes the current residual stream (set by the GEMM that produced it)
   bf16* patch_out_wb = nullptr;     // patch_out.proj.weight zero-padded to 64 rows (tensor-core patch-out)
   bf16* patch_out_wf = nullptr;     // the same with out_norm.scale folded in (fused out_norm)
+  bf16* patch_in_wb = nullptr;      // patch_in.proj.weight, columns permuted to (c, nh, nw) and padded to 64 (tensor-core patch-in)
   int ada_total = 0;
   CondWeights cw{};
   std::map<std::pair<int, int>, PosTables> pos_cache;
@@ -434,7 +435,14 @@ int forward_impl(KdbModel* m, int B, int H, int W, const float* x, const float* 
     if ((rc = launch_fold_norm_weights(m->fold_descs, m->n_fold, cond, st))) return rc;
   m->ss_valid = false;
   T* cur = reinterpret_cast<T*>(ws.xs[0]);
-  if ((rc = launch_patch_in<T>(x, sigma, sd, patch_in_w, cur, B, c.in_channels, H, W, c.patch_h, c.patch_w, c.width[0], st))) return rc;
+  if (std::is_same<T, bf16>::value && m->patch_in_wb != nullptr && tc_patch_in_supported(c.in_channels, c.patch_h, c.patch_w, c.width[0], W) &&
+      (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    m->ss_valid = m->fuse_norm;
+    if ((rc = launch_patch_in_tc(x, sigma, sd, m->patch_in_wb, reinterpret_cast<bf16*>(cur), B, H, W, c.width[0], m->ss_valid ? ws.rowss : nullptr, st)))
+      return rc;
+  } else if ((rc = launch_patch_in<T>(x, sigma, sd, patch_in_w, cur, B, c.in_channels, H, W, c.patch_h, c.patch_w, c.width[0], st))) {
+    return rc;
+  }
   if ((rc = tap<T>(m, "patch_in", cur, (int64_t)B * h0 * w0 * c.width[0], st))) return rc;
 
   int h = h0, w = w0;
@@ -613,6 +621,13 @@ int kdb_model_finalize(KdbModel* m, void* stream) {
   GET("out_norm.scale", &tmp, c.width[0]);
   GET("patch_out.proj.weight", &tmp, (int64_t)c.patch_h * c.patch_w * c.out_channels, c.width[0]);
 
+  m->patch_in_wb = nullptr;
+  if (c.in_channels == 3 && c.patch_h == 4 && c.patch_w == 4 && c.width[0] % 128 == 0) {
+    const float* piw = nullptr;
+    GET("patch_in.proj.weight", &piw, c.width[0], (int64_t)48);
+    if ((rc = dev_alloc(m, &m->patch_in_wb, (size_t)c.width[0] * 64))) return rc;
+    if ((rc = prepare_patch_in_weight(piw, m->patch_in_wb, c.width[0], st))) return rc;
+  }
   {   // zero-padded bf16 patch_out weight [64, C0]
     const int Np = c.patch_h * c.patch_w * c.out_channels, C0 = c.width[0];
     m->patch_out_wb = nullptr;

@@ -458,6 +458,168 @@ int pick_stages(int K, bool resid) {
 
 }  // namespace
 
+namespace {
+// ------------------------------------------------------------------------------------------------
+// patch_in on the tensor core (reference image_transformer_v2.py:586-595,723-724): tokens = TokenMerge 4x4 of c_in * x, then
+// Linear(48 -> C0).  The A tile [128 tokens x 64] is not a TMA box of the NCHW fp32 latent, so the four epilogue warps build
+// it: thread = token, 12 coalesced float4 loads (3 channels x 4 patch rows: consecutive tokens are consecutive 16-byte
+// pieces of an image row), * c_in, bf16, six 16-byte swizzled shared-memory stores.  K is ordered (c, nh, nw) -- the weight
+// copy made at finalize has its columns permuted to match and is zero-padded from 48 to 64.  One tcgen05.mma k-block, then
+// the usual TMEM -> bf16 staging tile -> TMA store epilogue, which also leaves sum(x^2) per row for the fused RMSNorm.
+// ------------------------------------------------------------------------------------------------
+struct PatchInParams {
+  const float* x;
+  const float* sigma;
+  float sd;
+  int64_t M;
+  int H, Wimg, th, tw, N;
+  float* ss_out;
+};
+
+__global__ void __launch_bounds__(192) patch_in_tc_kernel(const __grid_constant__ CUtensorMap tmw, const __grid_constant__ CUtensorMap tmc,
+                                                          const PatchInParams p) {
+  KDB_PDL_TRIGGER();
+  extern __shared__ uint8_t smem_raw[];
+  constexpr uint32_t IDESC = tc::idesc_bf16(BM, 128);
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = base;                       // [128 tokens x 64] bf16, SWIZZLE_128B
+  uint8_t* sW = base + A_STAGE_BYTES;       // [128 outputs x 64]
+  uint8_t* sC = sW + A_STAGE_BYTES;         // staging tile, two 64-column halves
+  uint64_t* w_full = reinterpret_cast<uint64_t*>(sC + 2 * SUB_TILE_BYTES);
+  uint64_t* a_full = w_full + 1;
+  uint64_t* tmem_full = w_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 3);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int n0 = blockIdx.y * 128;
+  if (threadIdx.x == 0) {
+    tc::tma_prefetch_desc(&tmw);
+    tc::tma_prefetch_desc(&tmc);
+    tc::mbar_init(w_full, 1);
+    tc::mbar_init(a_full, 128);
+    tc::mbar_init(tmem_full, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, 128);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (tc::elect_one()) {
+      tc::mbar_arrive_expect_tx(w_full, A_STAGE_BYTES);
+      tc::tma_load_2d(sW, &tmw, w_full, 0, n0);
+    }
+  } else if (warp == 1) {
+    if (tc::elect_one()) {
+      tc::mbar_wait(w_full, 0);
+      tc::mbar_wait(a_full, 0);
+      tc::tc_fence_after();
+      const uint64_t adesc = tc::smem_desc_k_sw128(tc::smem_u32(sA)), bdesc = tc::smem_desc_k_sw128(tc::smem_u32(sW));
+#pragma unroll
+      for (int k = 0; k < BK / 16; ++k) tc::umma_bf16(tmem, adesc + 2ull * k, bdesc + 2ull * k, IDESC, (uint32_t)(k != 0));
+      tc::umma_commit(tmem_full);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int64_t m = m0 + row;
+    // ---- gather: the token's 4x4x3 pixels
+    uint4 chunk[6];
+    if (m < p.M) {
+      const int per = p.th * p.tw;
+      const int b = (int)(m / per);
+      const int r = (int)(m - (int64_t)b * per);
+      const int ty = r / p.tw, tx = r - ty * p.tw;
+      float c_in = 1.f;
+      if (p.sd > 0.f) {
+        const float sg = __ldg(p.sigma + b);
+        c_in = rsqrtf(fmaf(sg, sg, p.sd * p.sd));
+      }
+      float4 px[12];
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int nh = 0; nh < 4; ++nh)
+          px[c * 4 + nh] = __ldg(reinterpret_cast<const float4*>(p.x + (((int64_t)b * 3 + c) * p.H + (ty * 4 + nh)) * p.Wimg + tx * 4));
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {          // chunk j = K columns 8j .. 8j+7 = (c = j / 2, nh = 2 (j & 1) and 2 (j & 1) + 1)
+        const float4 a = px[2 * j], bq = px[2 * j + 1];
+        chunk[j] = make_uint4(tc::pack_bf16x2(a.x * c_in, a.y * c_in), tc::pack_bf16x2(a.z * c_in, a.w * c_in), tc::pack_bf16x2(bq.x * c_in, bq.y * c_in),
+                              tc::pack_bf16x2(bq.z * c_in, bq.w * c_in));
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 6; ++j) chunk[j] = make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) *reinterpret_cast<uint4*>(sA + tc::sw128_offset(row, j)) = chunk[j];
+    *reinterpret_cast<uint4*>(sA + tc::sw128_offset(row, 6)) = make_uint4(0u, 0u, 0u, 0u);     // K 48..63: zero padding
+    *reinterpret_cast<uint4*>(sA + tc::sw128_offset(row, 7)) = make_uint4(0u, 0u, 0u, 0u);
+    tc::fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core's shared-memory reads
+    tc::mbar_arrive(a_full);
+    // ---- epilogue
+    tc::mbar_wait(tmem_full, 0);
+    tc::tc_fence_after();
+    float ss0 = 0.f, ss1 = 0.f;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      float v[64];
+      {
+        float t0[32], t1[32];
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 64);
+        tc::tmem_ld32(taddr, t0);
+        tc::tmem_ld32(taddr + 32, t1);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { v[i] = t0[i]; v[32 + i] = t1[i]; }
+      }
+#pragma unroll
+      for (int i = 0; i < 64; i += 2) {
+        ss0 = fmaf(v[i], v[i], ss0);
+        ss1 = fmaf(v[i + 1], v[i + 1], ss1);
+      }
+      uint8_t* cg = sC + g * SUB_TILE_BYTES;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint4*>(cg + tc::sw128_offset(row, j)) =
+            make_uint4(tc::pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]), tc::pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]),
+                       tc::pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]), tc::pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]));
+    }
+    if (p.ss_out != nullptr && m < p.M) p.ss_out[m * SS_PARTS + (n0 >> 7)] = ss0 + ss1;
+    tc::fence_proxy_async();
+    tc::named_barrier_sync(1, 128);
+    if (warp == 2 && tc::elect_one()) {
+      tc::tma_store_2d(&tmc, sC, n0, (int)m0);
+      tc::tma_store_2d(&tmc, sC + SUB_TILE_BYTES, n0 + 64, (int)m0);
+      tc::tma_store_commit();
+      tc::tma_store_wait_read();
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem, 128);
+  }
+}
+
+// W [N, 48] fp32 with columns (nh, nw, c) -> bf16 [N, 64] with columns (c, nh, nw), zero-padded
+__global__ void __launch_bounds__(256) patch_in_weight_kernel(const float* __restrict__ W, bf16* __restrict__ out, int N) {
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < N * 64; i += gridDim.x * 256) {
+    const int n = i >> 6, k = i & 63;
+    float v = 0.f;
+    if (k < 48) {
+      const int c = k >> 4, nh = (k >> 2) & 3, nw = k & 3;
+      v = W[(int64_t)n * 48 + (nh * 4 + nw) * 3 + c];
+    }
+    out[i] = __float2bfloat16(v);
+  }
+}
+
+}  // namespace
+
 static bool g_tc_disabled = [] {
   const char* e = getenv("KDB200_DISABLE_TC");
   return e != nullptr && e[0] == '1';
@@ -561,6 +723,45 @@ int launch_patch_out_tc(const bf16* xn, const bf16* W_pad, const float* x_in, co
   p.tw = Wimg / 4;
   KDB_REQUIRE(shape_ok(p.M, 64, C0), KDB_ERR_BAD_SHAPE, "patch_out_tc: unsupported shape");
   return launch_tc<64, TCE_PATCHOUT>(xn, W_pad, p, st);
+}
+
+bool tc_patch_in_supported(int Cin, int ph, int pw, int C0, int Wimg) {
+  return !g_tc_disabled && Cin == 3 && ph == 4 && pw == 4 && C0 % 128 == 0 && C0 <= 128 * SS_PARTS && Wimg % 4 == 0;
+}
+
+int prepare_patch_in_weight(const float* W, bf16* out, int C0, cudaStream_t st) {
+  patch_in_weight_kernel<<<(unsigned)ceil_div((int64_t)C0 * 64, 256), 256, 0, st>>>(W, out, C0);
+  KDB_LAUNCH_CHECK(F_CONVERT, st);
+  return 0;
+}
+
+int launch_patch_in_tc(const float* x, const float* sigma, float sigma_data, const bf16* W_perm, bf16* out, int B, int H, int Wimg, int C0,
+                       float* ss_out, cudaStream_t st) {
+  PatchInParams p{};
+  p.x = x;
+  p.sigma = sigma;
+  p.sd = sigma_data;
+  p.H = H;
+  p.Wimg = Wimg;
+  p.th = H / 4;
+  p.tw = Wimg / 4;
+  p.M = (int64_t)B * p.th * p.tw;
+  p.N = C0;
+  p.ss_out = ss_out;
+  KDB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, KDB_ERR_BAD_ARG, "patch_in_tc: input must be 16-byte aligned");
+  CUtensorMap tw, tcm;
+  int rc;
+  if ((rc = tmap_2d(&tw, W_perm, 64, (uint64_t)C0, 64, 128))) return rc;
+  if ((rc = tmap_2d(&tcm, out, (uint64_t)C0, (uint64_t)p.M, 64, BM))) return rc;
+  const size_t smem = 2 * A_STAGE_BYTES + 2 * SUB_TILE_BYTES + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    KDB_CUDA(cudaFuncSetAttribute(patch_in_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  patch_in_tc_kernel<<<dim3((unsigned)ceil_div(p.M, BM), (unsigned)(C0 / 128)), 192, smem, st>>>(tw, tcm, p);
+  KDB_LAUNCH_CHECK(F_PATCH_IN, st);
+  return 0;
 }
 
 bool tc_gemm_geglu_supported(int64_t M, int N2, int K, bool fused_norm) {

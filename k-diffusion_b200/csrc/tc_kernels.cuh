@@ -30,6 +30,12 @@ bool tc_patch_out_supported(int C0, int Cout, int ph, int pw, int Wimg);
 int launch_patch_out_tc(const bf16* xn, const bf16* W_pad, const float* x_in, const float* sigma, float sigma_data, float* out, int B, int H,
                         int Wimg, int C0, cudaStream_t st, const float* ss_in = nullptr);
 
+// patch_in (4x4 patches of a 3-channel fp32 latent) on the tensor core; W_perm = prepare_patch_in_weight(patch_in.proj.weight)
+bool tc_patch_in_supported(int Cin, int ph, int pw, int C0, int Wimg);
+int prepare_patch_in_weight(const float* W, bf16* out_perm, int C0, cudaStream_t st);
+int launch_patch_in_tc(const float* x, const float* sigma, float sigma_data, const bf16* W_perm, bf16* out, int B, int H, int Wimg, int C0,
+                       float* ss_out, cudaStream_t st);
+
 bool tc_attention_supported(int h, int w, int nh, int e, int attn_type, int attn_param);
 int launch_attention_tc(const bf16* qkv, bf16* out, int B, int h, int w, int nh, int e, int attn_type, int attn_param, int shift,
                         cudaStream_t st);
