@@ -314,7 +314,7 @@ def main():
                 traffic = (float(first["dram__bytes_read.sum [Mbyte]"]) + float(first["dram__bytes_write.sum [Mbyte]"])) * 1e6
                 traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the heaviest shape (" + first["launch"] +
                                 "), from the committed ncu --set full capture profiles/r1_ncu_full_summary.json; algorithmic bytes of that "
-                                "launch = A 33.6 MB + W 0.2 MB + out 50.3 MB")
+                                "launch = A 33.6 MB + W 0.2 MB + out 100.7 MB (the output is written once and mostly still in L2 when the kernel ends)")
             except (KeyError, ValueError, StopIteration):
                 pass
         roofline = {"bound": "tensor", "kernel": "gemm_tc_persist / gemm_tc_kernel (tcgen05 GEMM, all token-stream Linear layers: " +
@@ -324,8 +324,9 @@ def main():
                     "share_of_step": round(g_ms / total, 4), "traffic": traffic, "traffic_note": traffic_note, "by_shape": shapes,
                     "how": "CUDA events after every launch (on the launching stream) of one eager sample_heun with 5 Karras steps at the bench "
                            "batch; achieved = 2 x Linear MACs of those launches (reference flops.py accounting) / their summed device time",
-                    "note": "the K=128/256 GEMMs of the two high-resolution levels are bound by L2->SM operand bandwidth (A is re-read N/128 "
-                            "times), not by the tensor pipe: see DESIGN.md section 4"}
+                    "note": "K is only 128-1536, so each 128x128 tile carries 0.27-3 us of tensor work but a full fused epilogue (RMSNorm scale, GEGLU / "
+                            "cosine-sim + RoPE / residual, bf16 pack, TMA store); measured per-tile timelines show the epilogue warps' instruction "
+                            "issue, not the tensor pipe or memory, sets the tile period: see DESIGN.md section 4"}
         if world == 1:
             O, cpu_model, cores = cpu_port_setup()
             v, sample = cpu_port_time(O, cpu_model, 2, args.cpu_seconds)
