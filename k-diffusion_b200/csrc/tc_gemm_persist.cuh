@@ -1,20 +1,23 @@
 // tc_gemm_persist.cuh -- persistent, warp-specialised tcgen05 GEMM (included inside tc_kernels.cu's anonymous namespace).
 //
-// One CTA per SM loops over 128 x 128 output tiles (tile i -> m-block i / n_tiles, n-block i % n_tiles, so the CTAs of one
-// wave share A blocks in L2).  Nothing of a tile's fixed latency is on the critical path:
-//   warp 0      TMA producer: a STAGES-deep ring of SWIZZLE_128B stages that runs ahead across tiles; also fetches the
-//               residual tile of the tile it is loading for.
-//   warp 1      MMA issuer: tcgen05.mma into one of TWO TMEM accumulators (2 x 128 columns), commit -> frees the stage;
-//               after the last k-block commit -> tmem_full[acc].
-//   warps 2-9   epilogue (256 threads): warp w drains TMEM lanes 32*(w%4).., columns 64*((w-2)/4)..; releases the
-//               accumulator (tmem_empty[acc]) as soon as it is in registers, applies the fused epilogue, writes the row
-//               chunk into a swizzled staging tile, and one thread issues the TMA store.
-// Steady state per tile = max(TMA, MMA, epilogue) instead of their sum.
+// One CTA per SM (320 threads) walks a list of 128 x 128 output tiles:
+//   warp 0      TMA producer: a ring of SWIZZLE_128B stages that runs ahead across tiles.
+//   warp 1      MMA issuer: tcgen05.mma (M=128, N=128, K=16) into one of TWO TMEM accumulators (2 x 128 columns); a commit frees
+//               the ring stage, the commit after the last k-block signals tmem_full[acc].
+//   warps 2-9   two ping-pong epilogue groups of four warps; group g owns accumulator g, staging tile(s) g and every tile with
+//               (it & 1) == g.  Thread = accumulator row: tcgen05.ld (two passes of 64 columns), release the accumulator as soon
+//               as it is in registers, fused epilogue in fp32, bf16 pack into a swizzled staging tile, one thread issues the
+//               TMA store.  Residual / skip tiles are loaded by TMA INTO the staging tile and added in place.
+// Steady state per tile = max(TMA, MMA, epilogue) instead of their sum; measured, the epilogue groups set the pace for K <= 256
+// (see DESIGN.md section 4), so everything that is not arithmetic is kept off their critical path: waits for the previous TMA
+// store are deferred behind pass 0, table rows are prefetched, barrier waits are parked in hardware (suspend-time hint).
 //
-// Weight-resident mode (K <= 384): the skinny-K GEMMs of the high-resolution levels are bound by L2->SM operand traffic,
-// not by the tensor pipe (every 128x128 tile would re-fetch a 32 KB weight tile).  The grid is rounded to a multiple of
-// the number of n-blocks, so `tile += gridDim.x` keeps every CTA on ONE n-block; its [128 x K] weight block is loaded
-// once and stays in shared memory, and the ring streams A tiles only (half the bytes per tile, twice the stages).
+// Weight-resident mode (small K): a CTA owns 1-3 n-blocks whose [128 x K] weight blocks stay in shared memory for the whole
+// kernel; it walks m-tiles and uses ONE load of each A tile for all of its n-blocks.  The grid is rounded to a multiple of the
+// number of n-block groups.  Otherwise (streaming mode) both operands go through the ring, tile = blockIdx.x + it * gridDim.x.
+//
+// The kernel is launched programmatically (cudaLaunchAttributeProgrammaticStreamSerialization): barrier init, TMEM allocation and
+// the resident weight load happen before griddepcontrol.wait, i.e. while the previous kernel in the stream is still draining.
 #pragma once
 
 constexpr int P_BN = 128;
