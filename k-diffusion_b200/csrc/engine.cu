@@ -566,17 +566,22 @@ int kdb_model_finalize(KdbModel* m, void* stream) {
   // conditioning row order == execution order: down levels, mid, up levels (outermost last)
   for (int l = 0; l < n - 1; ++l) {
     m->down[l].resize(c.depth[l]);
-    for (int i = 0; i < c.depth[l]; ++i)
-      if ((rc = plan_layer(m, m->down[l][i], "down_levels." + std::to_string(l) + "." + std::to_string(i) + ".", l, i, &ada, st))) return rc;
+    for (int i = 0; i < c.depth[l]; ++i) {
+      rc = plan_layer(m, m->down[l][i], "down_levels." + std::to_string(l) + "." + std::to_string(i) + ".", l, i, &ada, st);
+      if (rc) return rc;
+    }
   }
   m->mid.resize(c.depth[n - 1]);
-  for (int i = 0; i < c.depth[n - 1]; ++i)
-    if ((rc = plan_layer(m, m->mid[i], "mid_level." + std::to_string(i) + ".", n - 1, i, &ada, st))) return rc;
+  for (int i = 0; i < c.depth[n - 1]; ++i) {
+    rc = plan_layer(m, m->mid[i], "mid_level." + std::to_string(i) + ".", n - 1, i, &ada, st);
+    if (rc) return rc;
+  }
   for (int l = n - 2; l >= 0; --l) {
     m->up[l].resize(c.depth[l]);
-    for (int i = 0; i < c.depth[l]; ++i)   // image_transformer_v2.py:697: up-level layer index continues after the down level
-      if ((rc = plan_layer(m, m->up[l][i], "up_levels." + std::to_string(l) + "." + std::to_string(i) + ".", l, i + c.depth[l], &ada, st)))
-        return rc;
+    for (int i = 0; i < c.depth[l]; ++i) {   // image_transformer_v2.py:697: up-level layer index continues after the down level
+      rc = plan_layer(m, m->up[l][i], "up_levels." + std::to_string(l) + "." + std::to_string(i) + ".", l, i + c.depth[l], &ada, st);
+      if (rc) return rc;
+    }
   }
   m->ada_total = ada;
   {
