@@ -235,6 +235,198 @@ def plan_dpmpp_2m(sig):
 
 
 # --------------------------------------------------------------------------------------------
+# Generic step plans (the remaining fixed-schedule samplers).  Every update of these solvers is a linear
+# combination, with host-computable scalar coefficients, of at most five image tensors, so a step is a short list of ops
+# over named buffers:
+#     ('eval',  out, src)                 out = D(src, sigma_k)      k-th entry of the step's 'evals'
+#     ('lin',   out, [(name, coef), ...]) out = sum coef * name      one kdb_solver_lincomb launch
+#     ('noise', out, sigma_from, sigma_to) out = noise_sampler(sigma_from, sigma_to)
+#     ('keep',  out, src)                 out aliases src (history of multistep methods; evals always write fresh buffers)
+# Plans are pure host math (verified on the CPU against reference trajectories in tests/test_host_logic.py).
+# --------------------------------------------------------------------------------------------
+
+def _log_mid(a, b):
+    return math.exp(0.5 * (math.log(a) + math.log(b)))
+
+
+def _euler_to(target, sigma):
+    """x + (x - den) / sigma * (target - sigma) as coefficients on (x, den)."""
+    r = (target - sigma) / sigma
+    return [('x', 1 + r), ('den', -r)]
+
+
+def _dpm2_ops(sigma, target):
+    """DPM-Solver-2 step from sigma to target (midpoint in log sigma), sampling.py:205-214 / :233-242."""
+    if target == 0:
+        return [('eval', 'den', 'x'), ('lin', 'x', _euler_to(target, sigma))], [sigma]
+    mid = _log_mid(sigma, target)
+    r1, c2 = (mid - sigma) / sigma, (target - sigma) / mid
+    return [('eval', 'den', 'x'), ('lin', 'x2', [('x', 1 + r1), ('den', -r1)]), ('eval', 'den2', 'x2'),
+            ('lin', 'x', [('x', 1.), ('x2', c2), ('den2', -c2)])], [sigma, mid]
+
+
+def plan_dpm_2(sig, s_churn=0., s_tmin=0., s_tmax=float('inf')):
+    steps = []
+    for i in range(len(sig) - 1):
+        gamma, sigma_hat, coef = _churn(sig, i, s_churn, s_tmin, s_tmax)
+        ops, evals = _dpm2_ops(sigma_hat, sig[i + 1])
+        steps.append(dict(i=i, gamma=gamma, sigma_hat=sigma_hat, churn=coef, ops=ops, evals=evals))
+    return steps
+
+
+def plan_dpm_2_ancestral(sig, eta=1., s_noise=1.):
+    steps = []
+    for i in range(len(sig) - 1):
+        down, up = get_ancestral_step(sig[i], sig[i + 1], eta=eta)
+        ops, evals = _dpm2_ops(sig[i], down)
+        if down != 0:
+            ops += [('noise', 'n', sig[i], sig[i + 1]), ('lin', 'x', [('x', 1.), ('n', s_noise * up)])]
+        steps.append(dict(i=i, sigma_hat=sig[i], ops=ops, evals=evals))
+    return steps
+
+
+def lms_coefficient(order, t, i, j):
+    """Integral over [t_i, t_{i+1}] of the j-th Lagrange basis polynomial through t_i, t_{i-1}, ... (sampling.py:247-257).
+    Degree <= order - 1, so 4-node Gauss-Legendre is exact (the reference uses scipy quad with epsrel 1e-4)."""
+    if order - 1 > i:
+        raise ValueError(f'Order {order} too high for step {i}')
+    a, b = t[i], t[i + 1]
+    nodes, weights = np.polynomial.legendre.leggauss(4)
+    tau = 0.5 * (b - a) * nodes + 0.5 * (b + a)
+    basis = np.ones_like(tau)
+    for k in range(order):
+        if k != j:
+            basis = basis * (tau - t[i - k]) / (t[i - j] - t[i - k])
+    return float(0.5 * (b - a) * np.dot(weights, basis))
+
+
+def plan_lms(sig, order=4):
+    if not 1 <= order <= 4:
+        raise ValueError('order must be between 1 and 4 (one lincomb launch takes x and four derivative buffers)')
+    steps = []
+    for i in range(len(sig) - 1):
+        cur = min(i + 1, order)
+        # derivative ring d0 (newest) .. d3: rotate names instead of moving data
+        names = [f'd{(i - j) % order}' for j in range(cur)]
+        ops = [('eval', 'den', 'x'), ('lin', names[0], [('x', 1 / sig[i]), ('den', -1 / sig[i])]),
+               ('lin', 'x', [('x', 1.)] + [(names[j], lms_coefficient(cur, sig, i, j)) for j in range(cur)])]
+        steps.append(dict(i=i, sigma_hat=sig[i], ops=ops, evals=[sig[i]]))
+    return steps
+
+
+def plan_dpmpp_2s_ancestral(sig, eta=1., s_noise=1.):
+    steps = []
+    for i in range(len(sig) - 1):
+        s = sig[i]
+        down, up = get_ancestral_step(s, sig[i + 1], eta=eta)
+        if down == 0:
+            ops, evals = [('eval', 'den', 'x'), ('lin', 'x', _euler_to(down, s))], [s]
+        else:
+            h = math.log(s) - math.log(down)                       # t_next - t with t = -log sigma
+            mid = math.exp(-(-math.log(s) + 0.5 * h))
+            ops = [('eval', 'den', 'x'), ('lin', 'x2', [('x', mid / s), ('den', -math.expm1(-0.5 * h))]), ('eval', 'den2', 'x2'),
+                   ('lin', 'x', [('x', down / s), ('den2', -math.expm1(-h))])]
+            evals = [s, mid]
+        if sig[i + 1] > 0:
+            ops += [('noise', 'n', s, sig[i + 1]), ('lin', 'x', [('x', 1.), ('n', s_noise * up)])]
+        steps.append(dict(i=i, sigma_hat=s, ops=ops, evals=evals))
+    return steps
+
+
+def _exp_step(sigma, down):
+    """(ratio, expm1(t - t_down)) of the exponential-integrator update towards sigma = down, with the down == 0 limit."""
+    if down == 0:
+        return 0., -1.
+    return down / sigma, math.expm1(math.log(down) - math.log(sigma))
+
+
+def plan_dpmpp_sde(sig, eta=1., s_noise=1., r=1 / 2):
+    steps = []
+    for i in range(len(sig) - 1):
+        s, s_next = sig[i], sig[i + 1]
+        if s_next == 0:
+            steps.append(dict(i=i, sigma_hat=s, ops=[('eval', 'den', 'x'), ('lin', 'x', _euler_to(0., s))], evals=[s]))
+            continue
+        t, t_next = -math.log(s), -math.log(s_next)
+        h = t_next - t
+        mid = math.exp(-(t + h * r))
+        fac = 1 / (2 * r)
+        sd, su = get_ancestral_step(s, mid, eta)
+        ratio1, e1 = _exp_step(s, sd)
+        sd2, su2 = get_ancestral_step(s, s_next, eta)
+        ratio2, e2 = _exp_step(s, sd2)
+        ops = [('eval', 'den', 'x'), ('noise', 'n', s, mid),
+               ('lin', 'x2', [('x', ratio1), ('den', -e1), ('n', s_noise * su)]), ('eval', 'den2', 'x2'), ('noise', 'n', s, s_next),
+               ('lin', 'x', [('x', ratio2), ('den', -e2 * (1 - fac)), ('den2', -e2 * fac), ('n', s_noise * su2)])]
+        steps.append(dict(i=i, sigma_hat=s, ops=ops, evals=[s, mid]))
+    return steps
+
+
+def plan_dpmpp_2m_sde(sig, eta=1., s_noise=1., solver_type='midpoint'):
+    if solver_type not in {'heun', 'midpoint'}:
+        raise ValueError('solver_type must be \'heun\' or \'midpoint\'')
+    steps, h_last = [], None
+    for i in range(len(sig) - 1):
+        s, s_next = sig[i], sig[i + 1]
+        if s_next == 0:
+            ops = [('eval', 'den', 'x'), ('lin', 'x', [('den', 1.)])]
+        else:
+            h = math.log(s) - math.log(s_next)
+            eta_h = eta * h
+            gain = -math.expm1(-h - eta_h)
+            terms = {'x': s_next / s * math.exp(-eta_h), 'den': gain}
+            if h_last is not None:
+                r = h_last / h
+                corr = (gain / (-h - eta_h) + 1) / r if solver_type == 'heun' else 0.5 * gain / r
+                terms['den'] += corr
+                terms['old'] = -corr
+            ops = [('eval', 'den', 'x')]
+            if eta:
+                ops.append(('noise', 'n', s, s_next))
+                terms['n'] = s_next * math.sqrt(-math.expm1(-2 * eta_h)) * s_noise
+            ops.append(('lin', 'x', list(terms.items())))
+            h_last = h
+        ops.append(('keep', 'old', 'den'))
+        steps.append(dict(i=i, sigma_hat=s, ops=ops, evals=[s]))
+    return steps
+
+
+def plan_dpmpp_3m_sde(sig, eta=1., s_noise=1.):
+    steps, h_1, h_2 = [], None, None
+    for i in range(len(sig) - 1):
+        s, s_next = sig[i], sig[i + 1]
+        h = None
+        if s_next == 0:
+            ops = [('eval', 'den', 'x'), ('lin', 'x', [('den', 1.)])]
+        else:
+            h = math.log(s) - math.log(s_next)
+            h_eta = h * (eta + 1)
+            terms = {'x': math.exp(-h_eta), 'den': -math.expm1(-h_eta)}
+            if h_2 is not None:
+                r0, r1 = h_1 / h, h_2 / h
+                phi_2 = math.expm1(-h_eta) / h_eta + 1
+                phi_3 = phi_2 / h_eta - 0.5
+                q, w = r0 / (r0 + r1), 1 / (r0 + r1)
+                ca, cb = phi_2 * (1 + q) - phi_3 * w, phi_2 * q - phi_3 * w      # coefficients of d1_0 and (minus) d1_1
+                terms['den'] += ca / r0
+                terms['old'] = -ca / r0 - cb / r1
+                terms['old2'] = cb / r1
+            elif h_1 is not None:
+                phi_2 = math.expm1(-h_eta) / h_eta + 1
+                terms['den'] += phi_2 / (h_1 / h)
+                terms['old'] = -phi_2 / (h_1 / h)
+            ops = [('eval', 'den', 'x')]
+            if eta:
+                ops.append(('noise', 'n', s, s_next))
+                terms['n'] = s_next * math.sqrt(-math.expm1(-2 * h * eta)) * s_noise
+            ops.append(('lin', 'x', list(terms.items())))
+        ops += ([('keep', 'old2', 'old')] if i > 0 else []) + [('keep', 'old', 'den')]     # aliases, no copies
+        h_1, h_2 = h, h_1
+        steps.append(dict(i=i, sigma_hat=s, ops=ops, evals=[s]))
+    return steps
+
+
+# --------------------------------------------------------------------------------------------
 # loop runner
 # --------------------------------------------------------------------------------------------
 
@@ -456,3 +648,110 @@ def sample_dpmpp_2m(model, x, sigmas, extra_args=None, callback=None, disable=No
 
     out = _run('dpmpp_2m', body, ev, xw, sig, (), callback)
     return _finish(out, x)
+
+
+# --------------------------------------------------------------------------------------------
+# the remaining fixed-schedule samplers, on the generic op plans.  Same evaluator, same graph runner and the
+# same kernels (`kdb_solver_lincomb`, the noise kernels) as the four samplers above; the plans are verified on the CPU
+# against reference trajectories (tests/test_host_logic.py).  GPU parity tests for these entry points land with round 2.
+# --------------------------------------------------------------------------------------------
+
+def _sample_ops(name, model, x, sigmas, plan_fn, extra_args, callback, disable, params, noise_sampler=None, churn_noise=0.):
+    xw, sig, extra_args = _prepare(x, sigmas, extra_args)
+    plan = plan_fn(sig)
+    needs_noise = any(op[0] == 'noise' for st in plan for op in st['ops'])
+    ours = isinstance(noise_sampler, (BrownianTreeNoiseSampler, PhiloxNoiseSampler))
+    stateless = isinstance(noise_sampler, BrownianTreeNoiseSampler)
+    churned = any(st.get('gamma', 0) > 0 for st in plan)
+    ev = _Evaluator(model, xw, extra_args, [s_ for st in plan for s_ in st['evals']])
+
+    def body(xc):
+        T = {'x': xc}
+        k = 0
+        for st in _progress(plan, disable):
+            if st.get('gamma', 0) > 0:
+                T['x'] = _native.lincomb([T['x'], torch.randn_like(T['x'])], [1., churn_noise * st['churn']])
+            first = True
+            for op in st['ops']:
+                kind = op[0]
+                if kind == 'eval':
+                    T[op[1]] = ev(k, T[op[2]])
+                    k += 1
+                    if first and callback is not None:
+                        callback({'x': T[op[2]], 'i': st['i'], 'sigma': sigmas[st['i']], 'sigma_hat': _scalar_like(sigmas, st['sigma_hat']),
+                                  'denoised': T[op[1]]})
+                    first = False
+                elif kind == 'lin':
+                    T[op[1]] = _native.lincomb([T[n] for n, _ in op[2]], [float(c) for _, c in op[2]])
+                elif kind == 'noise':    # our samplers take host floats (no sync); foreign callables get tensors like the reference
+                    args = (op[2], op[3]) if ours else (_scalar_like(sigmas, op[2]), _scalar_like(sigmas, op[3]))
+                    T[op[1]] = _native.f32c(noise_sampler(*args))
+                else:                    # 'keep': alias, evaluations always write fresh buffers
+                    T[op[1]] = T[op[2]]
+        return T['x']
+
+    # a graph replays the same noise every call: only legal without noise or with the Brownian tree (a pure function of sigma)
+    capturable = (not needs_noise or (ours and stateless)) and not churned
+    out = _run(name, body, ev, xw, sig, params + ((id(noise_sampler),) if needs_noise else ()), callback, noise_capturable=capturable)
+    return _finish(out, x)
+
+
+def _default_brownian(x, sigmas):
+    sigma_min, sigma_max = sigmas[sigmas > 0].min(), sigmas.max()
+    return BrownianTreeNoiseSampler(_native.f32c(x), sigma_min, sigma_max)
+
+
+@torch.no_grad()
+def sample_dpm_2(model, x, sigmas, extra_args=None, callback=None, disable=None, s_churn=0., s_tmin=0., s_tmax=float('inf'), s_noise=1.):
+    """A sampler inspired by DPM-Solver-2 and Algorithm 2 from Karras et al. (2022)  (reference sampling.py:187-214)."""
+    return _sample_ops('dpm_2', model, x, sigmas, lambda sig: plan_dpm_2(sig, s_churn, s_tmin, s_tmax), extra_args, callback, disable,
+                       (s_churn, s_tmin, s_tmax, s_noise), churn_noise=s_noise)
+
+
+@torch.no_grad()
+def sample_dpm_2_ancestral(model, x, sigmas, extra_args=None, callback=None, disable=None, eta=1., s_noise=1., noise_sampler=None):
+    """Ancestral sampling with DPM-Solver second-order steps  (reference sampling.py:217-244)."""
+    noise_sampler = default_noise_sampler(_native.f32c(x)) if noise_sampler is None else noise_sampler
+    return _sample_ops('dpm_2_a', model, x, sigmas, lambda sig: plan_dpm_2_ancestral(sig, eta, s_noise), extra_args, callback, disable,
+                       (eta, s_noise), noise_sampler)
+
+
+@torch.no_grad()
+def sample_lms(model, x, sigmas, extra_args=None, callback=None, disable=None, order=4):
+    """Linear multistep (Adams-Bashforth in sigma)  (reference sampling.py:247-277)."""
+    return _sample_ops('lms', model, x, sigmas, lambda sig: plan_lms(sig, order), extra_args, callback, disable, (order,))
+
+
+@torch.no_grad()
+def sample_dpmpp_2s_ancestral(model, x, sigmas, extra_args=None, callback=None, disable=None, eta=1., s_noise=1., noise_sampler=None):
+    """Ancestral sampling with DPM-Solver++(2S) second-order steps  (reference sampling.py:508-539)."""
+    noise_sampler = default_noise_sampler(_native.f32c(x)) if noise_sampler is None else noise_sampler
+    return _sample_ops('dpmpp_2s_a', model, x, sigmas, lambda sig: plan_dpmpp_2s_ancestral(sig, eta, s_noise), extra_args, callback, disable,
+                       (eta, s_noise), noise_sampler)
+
+
+@torch.no_grad()
+def sample_dpmpp_sde(model, x, sigmas, extra_args=None, callback=None, disable=None, eta=1., s_noise=1., noise_sampler=None, r=1 / 2):
+    """DPM-Solver++ (stochastic)  (reference sampling.py:542-581)."""
+    noise_sampler = _default_brownian(x, sigmas) if noise_sampler is None else noise_sampler
+    return _sample_ops('dpmpp_sde', model, x, sigmas, lambda sig: plan_dpmpp_sde(sig, eta, s_noise, r), extra_args, callback, disable,
+                       (eta, s_noise, r), noise_sampler)
+
+
+@torch.no_grad()
+def sample_dpmpp_2m_sde(model, x, sigmas, extra_args=None, callback=None, disable=None, eta=1., s_noise=1., noise_sampler=None,
+                        solver_type='midpoint'):
+    """DPM-Solver++(2M) SDE  (reference sampling.py:610-652)."""
+    if solver_type not in {'heun', 'midpoint'}:
+        raise ValueError('solver_type must be \'heun\' or \'midpoint\'')
+    noise_sampler = _default_brownian(x, sigmas) if noise_sampler is None else noise_sampler
+    return _sample_ops('dpmpp_2m_sde', model, x, sigmas, lambda sig: plan_dpmpp_2m_sde(sig, eta, s_noise, solver_type), extra_args, callback,
+                       disable, (eta, s_noise, solver_type), noise_sampler)
+
+
+@torch.no_grad()
+def sample_dpmpp_3m_sde(model, x, sigmas, extra_args=None, callback=None, disable=None, eta=1., s_noise=1., noise_sampler=None):
+    """DPM-Solver++(3M) SDE  (reference sampling.py:655-703)."""
+    noise_sampler = _default_brownian(x, sigmas) if noise_sampler is None else noise_sampler
+    return _sample_ops('dpmpp_3m_sde', model, x, sigmas, lambda sig: plan_dpmpp_3m_sde(sig, eta, s_noise), extra_args, callback, disable,
+                       (eta, s_noise), noise_sampler)

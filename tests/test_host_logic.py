@@ -85,6 +85,99 @@ def test_step_plans_reproduce_reference_trajectories():
                  z["sample_euler_ancestral_eta05"], rtol=1e-4, atol=1e-5)
 
 
+def _exec_ops(plan, model, x, noise=None):
+    """CPU interpreter of the generic op plans (what the lincomb kernel and the evaluator do), for plan verification only."""
+    T = {"x": x.clone()}
+    B = x.shape[0]
+    it = iter(noise) if noise is not None else None
+    for st in plan:
+        k = 0
+        for op in st["ops"]:
+            if op[0] == "eval":
+                T[op[1]] = model(T[op[2]], torch.full([B], st["evals"][k]))
+                k += 1
+            elif op[0] == "lin":
+                T[op[1]] = sum(np.float32(c) * T[n] for n, c in op[2])
+            elif op[0] == "noise":
+                T[op[1]] = next(it)
+            elif op[0] == "keep":
+                T[op[1]] = T[op[2]]
+            else:
+                raise AssertionError(op)
+        assert k == len(st["evals"])
+    return T["x"]
+
+
+def test_generic_op_plans_reproduce_reference_trajectories():
+    """SURVEY 8f.1 samplers: host plans vs trajectories recorded from the reference (oracle/make_golden_next.py)."""
+    z = load_npz("toy_next_samplers.npz")
+    toy2 = lambda x, s, **kw: x / (1 + s[:, None, None, None] ** 2) + 0.1 * torch.tanh(x)
+    sig = S.host_sigmas(z["sigmas"])
+    x, nz = z["x"], z["noise"]
+    cases = [
+        ("sample_dpm_2", S.plan_dpm_2(sig), None),
+        ("sample_lms", S.plan_lms(sig), None),
+        ("sample_lms_order2", S.plan_lms(sig, order=2), None),
+        ("sample_dpm_2_ancestral", S.plan_dpm_2_ancestral(sig), nz),
+        ("sample_dpm_2_ancestral_eta05", S.plan_dpm_2_ancestral(sig, eta=0.5, s_noise=0.9), nz),
+        ("sample_dpmpp_2s_ancestral", S.plan_dpmpp_2s_ancestral(sig), nz),
+        ("sample_dpmpp_2s_ancestral_eta0", S.plan_dpmpp_2s_ancestral(sig, eta=0.), nz),
+        ("sample_dpmpp_sde", S.plan_dpmpp_sde(sig), nz),
+        ("sample_dpmpp_sde_r03", S.plan_dpmpp_sde(sig, eta=0.7, s_noise=0.9, r=0.3), nz),
+        ("sample_dpmpp_2m_sde", S.plan_dpmpp_2m_sde(sig), nz),
+        ("sample_dpmpp_2m_sde_heun", S.plan_dpmpp_2m_sde(sig, eta=0.6, solver_type="heun"), nz),
+        ("sample_dpmpp_2m_sde_eta0", S.plan_dpmpp_2m_sde(sig, eta=0.), nz),
+        ("sample_dpmpp_3m_sde", S.plan_dpmpp_3m_sde(sig), nz),
+        ("sample_dpmpp_3m_sde_eta05", S.plan_dpmpp_3m_sde(sig, eta=0.5, s_noise=0.8), nz),
+    ]
+    for key, plan, noise in cases:
+        assert_close(_exec_ops(plan, toy2, x, noise), z[key], rtol=1e-4, atol=2e-5, what=key)
+        assert all(len(terms) <= 6 for st in plan for op in st["ops"] if op[0] == "lin" for terms in [op[2]])   # one lincomb launch each
+    assert sum(len(st["evals"]) for st in S.plan_dpm_2(sig)) == 19 and sum(len(st["evals"]) for st in S.plan_lms(sig)) == 10
+    with pytest.raises(ValueError):
+        S.plan_dpmpp_2m_sde(sig, solver_type="euler")
+    with pytest.raises(ValueError):
+        S.plan_lms(sig, order=5)
+
+
+def test_generic_sampler_entry_points_with_stubbed_kernels(monkeypatch):
+    """The executor behind sample_dpm_2 / lms / dpmpp_*_sde, driven end to end on the CPU by replacing the three native
+    primitives it touches with torch one-liners (test-only stubs; the product has no CPU path).  Checks op interpretation,
+    evaluation order, callback payloads and the noise-sampler calling convention against the reference trajectories."""
+    from k_diffusion import _native
+    monkeypatch.setattr(_native, "require_cuda", lambda *t: None)
+    monkeypatch.setattr(_native, "f32c", lambda t: t.to(torch.float32).contiguous())
+    monkeypatch.setattr(_native, "lincomb", lambda ts, cs, out=None: sum(np.float32(c) * t for t, c in zip(ts, cs)))
+    z = load_npz("toy_next_samplers.npz")
+    toy2 = lambda x, s, **kw: x / (1 + s[:, None, None, None] ** 2) + 0.1 * torch.tanh(x)
+    x, sig, nz = z["x"], z["sigmas"], z["noise"]
+
+    def ns():
+        it = iter(nz)
+        return lambda a, b: next(it)
+
+    runs = {
+        "sample_dpm_2": lambda: S.sample_dpm_2(toy2, x, sig, disable=True),
+        "sample_lms": lambda: S.sample_lms(toy2, x, sig, disable=True),
+        "sample_dpm_2_ancestral_eta05": lambda: S.sample_dpm_2_ancestral(toy2, x, sig, disable=True, eta=0.5, s_noise=0.9, noise_sampler=ns()),
+        "sample_dpmpp_2s_ancestral": lambda: S.sample_dpmpp_2s_ancestral(toy2, x, sig, disable=True, noise_sampler=ns()),
+        "sample_dpmpp_sde_r03": lambda: S.sample_dpmpp_sde(toy2, x, sig, disable=True, eta=0.7, s_noise=0.9, r=0.3, noise_sampler=ns()),
+        "sample_dpmpp_2m_sde_heun": lambda: S.sample_dpmpp_2m_sde(toy2, x, sig, disable=True, eta=0.6, solver_type="heun", noise_sampler=ns()),
+        "sample_dpmpp_3m_sde": lambda: S.sample_dpmpp_3m_sde(toy2, x, sig, disable=True, noise_sampler=ns()),
+    }
+    for key, run in runs.items():
+        assert_close(run(), z[key], rtol=1e-4, atol=2e-5, what=key)
+    seen = []
+    S.sample_dpmpp_2m_sde(toy2, x, sig, disable=True, noise_sampler=ns(), callback=seen.append)
+    assert [c["i"] for c in seen] == list(range(10)) and set(seen[0]) == {"x", "i", "sigma", "sigma_hat", "denoised"}
+    assert torch.equal(seen[0]["x"], x) and float(seen[3]["sigma"]) == float(sig[3])
+    calls = []
+    S.sample_dpmpp_sde(toy2, x, sig, disable=True, noise_sampler=lambda a, b: calls.append((float(a), float(b))) or nz[0])
+    assert len(calls) == 18 and all(a > b for a, b in calls)        # two draws per step except the final Euler step, sigma decreasing
+    with pytest.raises(ValueError):
+        S.sample_dpmpp_2m_sde(toy2, x, sig, solver_type="euler")
+
+
 def test_plan_details():
     sig = S.host_sigmas(S.get_sigmas_karras(50, 1e-2, 160))
     heun = S.plan_heun(sig)

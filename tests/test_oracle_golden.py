@@ -54,6 +54,42 @@ def test_nonlinear_toy_samplers_bit_exact():
     assert torch.equal(got, z["sample_euler_ancestral_eta05"])
 
 
+def test_next_row_samplers_against_reference():
+    """SURVEY 8(f) row 1 (not yet on the CUDA path): oracle restatements pinned against reference trajectories."""
+    z = load_npz("toy_next_samplers.npz")
+    toy2 = lambda x, s, **kw: x / (1 + s[:, None, None, None] ** 2) + 0.1 * torch.tanh(x)
+    x, sig = z["x"], z["sigmas"]
+
+    def ns():
+        it = iter(z["noise"])
+        return lambda a, b: next(it)
+
+    cases = {
+        "sample_dpm_2": lambda: O.sample_dpm_2(toy2, x, sig),
+        "sample_dpm_2_ancestral": lambda: O.sample_dpm_2_ancestral(toy2, x, sig, noise_sampler=ns()),
+        "sample_dpm_2_ancestral_eta05": lambda: O.sample_dpm_2_ancestral(toy2, x, sig, eta=0.5, s_noise=0.9, noise_sampler=ns()),
+        "sample_dpmpp_2s_ancestral": lambda: O.sample_dpmpp_2s_ancestral(toy2, x, sig, noise_sampler=ns()),
+        "sample_dpmpp_2s_ancestral_eta0": lambda: O.sample_dpmpp_2s_ancestral(toy2, x, sig, eta=0.0, noise_sampler=ns()),
+        "sample_dpmpp_sde": lambda: O.sample_dpmpp_sde(toy2, x, sig, ns()),
+        "sample_dpmpp_sde_r03": lambda: O.sample_dpmpp_sde(toy2, x, sig, ns(), eta=0.7, s_noise=0.9, r=0.3),
+        "sample_dpmpp_2m_sde": lambda: O.sample_dpmpp_2m_sde(toy2, x, sig, ns()),
+        "sample_dpmpp_2m_sde_heun": lambda: O.sample_dpmpp_2m_sde(toy2, x, sig, ns(), eta=0.6, solver_type="heun"),
+        "sample_dpmpp_2m_sde_eta0": lambda: O.sample_dpmpp_2m_sde(toy2, x, sig, ns(), eta=0.0),
+        "sample_dpmpp_3m_sde": lambda: O.sample_dpmpp_3m_sde(toy2, x, sig, ns()),
+        "sample_dpmpp_3m_sde_eta05": lambda: O.sample_dpmpp_3m_sde(toy2, x, sig, ns(), eta=0.5, s_noise=0.8),
+    }
+    for name, run in cases.items():       # same torch op sequence as the reference on the same CPU -> identical bits
+        assert torch.equal(run(), z[name]), name
+    # linear multistep: the reference integrates the Lagrange basis with scipy quad (epsrel 1e-4), the oracle exactly
+    assert_close(O.sample_lms(toy2, x, sig), z["sample_lms"], rtol=1e-5, atol=1e-5, what="sample_lms")
+    assert_close(O.sample_lms(toy2, x, sig, order=2), z["sample_lms_order2"], rtol=1e-5, atol=1e-5, what="sample_lms order 2")
+    import pytest
+    with pytest.raises(ValueError):
+        O.lms_coefficient(3, sig.numpy(), 1, 0)
+    with pytest.raises(ValueError):
+        O.sample_dpmpp_2m_sde(toy2, x, sig, ns(), solver_type="euler")
+
+
 def _discrete():
     betas = torch.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000) ** 2
     ac = torch.cumprod(1 - betas, 0)
