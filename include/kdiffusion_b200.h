@@ -160,7 +160,12 @@ size_t kdb_model_workspace_bytes(const KdbModel* m, int precision, int batch, in
  *   sigma_data <= 0: the raw inner model F(x, sigma) (image_transformer_v2.py:721-762).
  * cond holds rows from kdb_model_conditioning for the same sigma/conditioning; sample b reads the
  * row at cond + b * cond_batch_stride (floats): cond_stride for per-sample rows, 0 when the whole
- * batch shares one (sigma, conditioning) tuple -- the usual case inside a sampler. */
+ * batch shares one (sigma, conditioning) tuple -- the usual case inside a sampler.  With a shared row (and the bf16
+ * precision) every AdaRMSNorm is fused into the neighbouring GEMMs: the channel scales are folded into per-evaluation
+ * copies of the qkv / up_proj weights and 1/rms comes from row statistics the producing GEMM leaves in the workspace.
+ * All launches are stream-ordered on `stream` (several with programmatic dependent launch, i.e. a kernel's prologue may
+ * overlap the tail of its predecessor on the same stream); nothing is allocated or synchronised, so the call can be
+ * captured into a CUDA graph once the position tables of this token grid exist (first call outside capture). */
 int kdb_model_forward(KdbModel* m, int precision, int batch, int height, int width,
                       const float* x, const float* sigma, float sigma_data,
                       const float* cond, int64_t cond_batch_stride, float* out,
