@@ -345,6 +345,8 @@ __global__ void __launch_bounds__(160, MODE == MODE_WINDOW ? 4 : 2) attn_tc_kern
   }
 }
 
+#include "tc_attention_persist.cuh"
+
 constexpr size_t ATTN_SMEM = 5 * TILE_BYTES + 1024 + 128;          // GLOBAL
 constexpr size_t ATTN_SMEM_WINDOW = 3 * TILE_BYTES + 1024 + 128;   // WINDOW (P aliases Q,K)
 
@@ -407,6 +409,32 @@ int launch_attention_tc(const bf16* qkv, bf16* out, int B, int h, int w, int nh,
       attr_w = true;
     }
     p.nblk = 1;
+    const char* pe = getenv("KDB200_ATTN_PERSIST");      // experimental persistent variant (default off), read per call so tests can A/B
+    if (pe != nullptr && pe[0] == '1') {
+      static bool attr_p = false;
+      if (!attr_p) {
+        KDB_CUDA(cudaFuncSetAttribute(attn_window_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATTN_SMEM_WINDOW_PERSIST));
+        attr_p = true;
+      }
+      const int n_units = B * (h / 8) * (w / 8) * (nh / 2);
+      int sms = 0, dev = 0;
+      KDB_CUDA(cudaGetDevice(&dev));
+      KDB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      const int grid_p = n_units < 2 * sms ? n_units : 2 * sms;
+      cudaLaunchConfig_t lc{};
+      lc.gridDim = dim3((unsigned)grid_p);
+      lc.blockDim = dim3(160);
+      lc.dynamicSmemBytes = ATTN_SMEM_WINDOW_PERSIST;
+      lc.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      lc.attrs = attr;
+      lc.numAttrs = 1;
+      KDB_CUDA(cudaLaunchKernelEx(&lc, attn_window_persist_kernel, tm, p, n_units));
+      KDB_LAUNCH_CHECK(F_ATTN_TC, st);
+      return 0;
+    }
     dim3 grid((unsigned)((h / 8) * (w / 8)), (unsigned)(nh / 2), (unsigned)B);
     KDB_CUDA(launch_attn<MODE_WINDOW>(grid, ATTN_SMEM_WINDOW, st, tm, tm, p));
   } else if (attn_type == KDB_ATTN_NEIGHBORHOOD) {
