@@ -1,5 +1,5 @@
 // tc_attention_persist.cuh -- EXPERIMENTAL persistent shifted-window attention (included inside tc_attention.cu's anonymous
-// namespace; selected only with KDB200_ATTN_PERSIST=1, default off; first GPU run pending -- see tests/test_gpu_next_samplers.py).
+// namespace; selected only with KDB200_ATTN_PERSIST=1, default off; first GPU run pending -- see tests/test_gpu_zz_experimental.py).
 //
 // Motivation (profiles/r1_ncu_full_summary.json): attn_tc_kernel<WINDOW> runs one (window, head pair) per CTA as a
 // serial chain TMA -> S MMA -> softmax -> O MMA -> store, four CTAs per SM; 31 % of a softmax warp's life is the wait for
