@@ -16,7 +16,7 @@ from conftest import assert_close, load_npz
 from oracle import kdiff_oracle as O
 from test_gpu_parity import build
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first GPU run of the 8f.1 entry points (no GPU minutes were left to confirm them)")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180), pytest.mark.xfail(strict=False, reason="first GPU run of the 8f.1 entry points (no GPU minutes were left to confirm them)")]
 S = K.sampling
 DEV = "cuda"
 toy2 = lambda x, s, **kw: x / (1 + s[:, None, None, None] ** 2) + 0.1 * torch.tanh(x)
