@@ -260,3 +260,17 @@ def test_shard_helpers():
     full = P.sample_seeds(7, 0, 16)
     assert len(set(full)) == 16 and all(0 <= s < 2 ** 63 for s in full)
     assert P.sample_seeds(7, 4, 9) == full[4:9] and P.sample_seeds(8, 0, 16) != full
+
+
+def test_experimental_attention_barrier_protocol_model():
+    """tools/attn_protocol_sim.py: randomised interleavings of the persistent window-attention kernel's mbarrier protocol
+    (try_wait.parity semantics) must never alias a phase, deadlock, or refill a live buffer."""
+    import importlib.util
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("attn_protocol_sim", ROOT / "tools" / "attn_protocol_sim.py")
+    sim = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sim)
+    for n_local in (0, 1, 2, 3, 4, 7):
+        for seed in range(40):
+            assert sim.run(n_local, seed)
+
