@@ -1,14 +1,18 @@
 #!/usr/bin/env python
 """bench.py -- images/sec of the k-diffusion sampling hot path on B200.
 
-One "step" = one complete `sample_heun` call (50 Karras steps = 99 denoiser evaluations) over one
-batch of 32 synthetic 256x256x3 latents per GPU on the image_transformer_v2 oxford-flowers
-shifted-window model (BASELINE.json configs[1]).  Weak scaling: every rank samples its own 32.
+One "step" = one complete sampler call over one batch of synthetic latents per GPU on the image_transformer_v2 denoiser.
+`--config` selects the BASELINE.json workload (default cfg2 = configs[1], the one the headline metric is quoted on):
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]             # N>1: launched by torch.distributed.run
-    python bench.py --impl reference ...                            # the reference algorithm's CPU port (oracle/)
+    cfg2  sample_heun 50 steps (99 evaluations), 256x256 shifted-window model, batch 32 per GPU
+    cfg3  sample_dpmpp_2m 25 steps, 256x256 neighbourhood-attention model, batch 64 per GPU
+    cfg4  sample_euler_ancestral 50 steps + BrownianTreeNoiseSampler, 256x256 neighbourhood model, batch 32 per GPU (256 over 8)
+    cfg5  sample_heun 50 steps, 512x512 hourglass depths [2,2,4] widths [256,512,1024], batch 16 per GPU (128 over 8)
 
-Prints ONE JSON line on rank 0 (see the contract in the task statement / DESIGN.md section 6).
+    python bench.py [--config cfgN] [--gpus N] [--steps K] [--warmup W]   # N>1: launched by torch.distributed.run
+    python bench.py --impl reference ...                                  # the reference algorithm's CPU port (oracle/)
+
+Weak scaling: every rank samples its own batch.  Prints ONE JSON line on rank 0 (contract: task statement / DESIGN.md section 6).
 """
 import argparse
 import json
@@ -27,53 +31,69 @@ for p in (str(ROOT), str(ROOT / "k-diffusion_b200")):
 
 import torch
 
-METRIC = "images/sec (256x256, Heun 50-step)"
 UNIT = "images/s"
-CFG_FIXTURE = ROOT / "tests" / "golden" / "cfg2_sw256_shapes.json"     # reference config_oxford_flowers_shifted_window.json + defaults
-SAMPLER_STEPS, SIGMA_MIN, SIGMA_MAX, RES, PER_GPU_BATCH = 50, 1e-2, 160.0, 256, 32
-NFE = 2 * SAMPLER_STEPS - 1
+SIGMA_MIN, SIGMA_MAX = 1e-2, 160.0
+_NA_RAW = {"model": {"type": "image_transformer_v2", "input_channels": 3, "input_size": [256, 256], "patch_size": [4, 4],
+                     "depths": [2, 2, 4], "widths": [128, 256, 512], "loss_config": "karras", "loss_weighting": "soft-min-snr",
+                     "dropout_rate": [0.0, 0.0, 0.1], "augment_prob": 0.0, "sigma_data": 0.5, "sigma_min": 1e-2, "sigma_max": 160,
+                     "sigma_sample_density": {"type": "cosine-interpolated"}}}      # reference configs/config_oxford_flowers.json
+CONFIGS = {
+    "cfg2": dict(fixture="cfg2_sw256_shapes.json", sampler="heun", steps=50, res=256, batch=32,
+                 metric="images/sec (256x256, Heun 50-step)",
+                 what="image_transformer_v2 256x256 (oxford_flowers shifted-window config)"),
+    "cfg3": dict(raw=_NA_RAW, sampler="dpmpp_2m", steps=25, res=256, batch=64,
+                 metric="images/sec (256x256, DPM++(2M) 25-step, neighborhood attention)",
+                 what="image_transformer_v2 256x256 (oxford_flowers config: 7x7 neighborhood attention x2 levels + global)"),
+    "cfg4": dict(raw=_NA_RAW, sampler="euler_ancestral", steps=50, res=256, batch=32,
+                 metric="images/sec (256x256, Euler-ancestral 50-step + BrownianTree, neighborhood attention)",
+                 what="image_transformer_v2 256x256 (oxford_flowers config, neighborhood attention), BrownianTreeNoiseSampler with one seed per image"),
+    "cfg5": dict(raw={"model": dict(_NA_RAW["model"], input_size=[512, 512], widths=[256, 512, 1024], depths=[2, 2, 4],
+                                    dropout_rate=[0.0, 0.0, 0.0])},
+                 sampler="heun", steps=50, res=512, batch=16, metric="images/sec (512x512, Heun 50-step, widths 256/512/1024)",
+                 what="image_transformer_v2 512x512 hourglass depths [2,2,4] widths [256,512,1024] (neighborhood x2 + global, S=1024)"),
+}
+SAMPLER_NAME = {"heun": "sample_heun", "dpmpp_2m": "sample_dpmpp_2m", "euler_ancestral": "sample_euler_ancestral"}
+
+
+def nfe_of(sampler, steps):
+    return 2 * steps - 1 if sampler == "heun" else steps
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=None, help="timed sampler calls (default 5; 3 for cfg5)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch (default: the BASELINE config)")
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: the BASELINE config's)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--no-extras", action="store_true", help="skip the roofline and cpu_baseline legs")
+    ap.add_argument("--no-extras", action="store_true", help="skip the roofline, parity and cpu_baseline legs")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
-    return ap.parse_args()
+    ap.add_argument("--parity-seconds", type=float, default=25.0, help="CPU budget of the parity leg (oracle run of one image)")
+    args = ap.parse_args()
+    args.wl = CONFIGS[args.config]
+    if args.batch is None:
+        args.batch = args.wl["batch"]
+    if args.steps is None:
+        args.steps = 3 if args.config == "cfg5" else 5
+    return args
 
 
-def workload_config(n_gpus, batch):
-    return {"workload": f"sample_heun {SAMPLER_STEPS} steps ({NFE} model evaluations), image_transformer_v2 {RES}x{RES} "
-                        "(oxford_flowers shifted-window config), synthetic seeded weights, Karras schedule rho=7 "
-                        f"sigma [{SIGMA_MIN}, {SIGMA_MAX}], batch {batch} per GPU",
-            "sampler": "heun", "sampler_steps": SAMPLER_STEPS, "nfe_per_image": NFE, "resolution": RES,
+def raw_model_config(wl):
+    if "fixture" in wl:
+        return json.loads((ROOT / "tests" / "golden" / wl["fixture"]).read_text())["config"]
+    return json.loads(json.dumps(wl["raw"]))
+
+
+def workload_config(args, n_gpus):
+    wl, batch = args.wl, args.batch
+    nfe = nfe_of(wl["sampler"], wl["steps"])
+    return {"workload": f"{args.config}: {SAMPLER_NAME[wl['sampler']]} {wl['steps']} steps ({nfe} model evaluations), {wl['what']}, synthetic seeded "
+                        f"weights, Karras schedule rho=7 sigma [{SIGMA_MIN}, {SIGMA_MAX}], batch {batch} per GPU",
+            "baseline_config": args.config, "sampler": wl["sampler"], "sampler_steps": wl["steps"], "nfe_per_image": nfe, "resolution": wl["res"],
             "per_gpu_batch": batch, "global_batch": batch * n_gpus, "parallelism": f"dp{n_gpus} (batch shards, no per-step collective)",
             "l2": "256 MiB buffer rewritten between timed steps; per-step activation working set also exceeds the 126 MB L2"}
-
-
-def model_config():
-    return json.loads(CFG_FIXTURE.read_text())["config"]
-
-
-def linear_macs_per_image(mcfg):
-    """MACs of every nn.Linear on the token stream per image per model evaluation (reference flops.py:40-41)."""
-    widths, depths, d_ffs = mcfg["widths"], mcfg["depths"], mcfg["d_ffs"]
-    ph, pw = mcfg["patch_size"]
-    t = (mcfg["input_size"][0] // ph) * (mcfg["input_size"][1] // pw)
-    total, n = 0, len(widths)
-    for i, (w, d, f) in enumerate(zip(widths, depths, d_ffs)):
-        layers = d * (1 if i == n - 1 else 2)
-        attn = 0 if mcfg["self_attns"][i]["type"] == "none" else 4 * w * w
-        total += layers * t * (attn + 3 * w * f)
-        if i < n - 1:
-            total += (t // 4) * 4 * w * widths[i + 1] * 2
-        t //= 4
-    return total
 
 
 # ------------------------------------------------------------------------------------------------
@@ -121,15 +141,32 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU legs (the ONLY place bench.py touches oracle/)
 # ------------------------------------------------------------------------------------------------
-def cpu_port_setup():
+def oracle_model(wl, inner=None):
+    """(oracle module, oracle denoiser) with the synthetic weights of seed 1 (the recipe depends on key/shape/seed only)."""
+    import k_diffusion as K
     from oracle import kdiff_oracle as O
     from oracle.fixtures import synth_sd
-    meta = json.loads(CFG_FIXTURE.read_text())
-    sd = synth_sd(meta["shapes"], 1)
-    model = O.make_denoiser(sd, meta["config"]["model"])
+    cfg = K.config.load_config(raw_model_config(wl))
+    if inner is None:
+        inner = K.config.make_model(cfg)
+    sd = synth_sd({k: list(v.shape) for k, v in inner.state_dict().items()}, 1)
+    return O, O.make_denoiser(sd, cfg["model"])
+
+
+def oracle_sample(O, model, wl, x, sigmas, seeds=None):
+    if wl["sampler"] == "heun":
+        return O.sample_heun(model, x, sigmas)
+    if wl["sampler"] == "dpmpp_2m":
+        return O.sample_dpmpp_2m(model, x, sigmas)
+    g = torch.Generator().manual_seed(7)          # timing only: any unit-normal stream costs the same
+    return O.sample_euler_ancestral(model, x, sigmas, noise_sampler=lambda a, b: torch.randn(x.shape, generator=g))
+
+
+def cpu_port_setup(wl):
+    O, model = oracle_model(wl)
     # pick the torch thread count that is actually fastest on this host (all-cores oversubscribes cgroup-limited boxes)
     avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    x = torch.randn(1, 3, RES, RES)
+    x = torch.randn(1, 3, wl["res"], wl["res"])
     best, cores = None, 1
     for n in sorted({c for c in (8, 16, 32, 64, avail) if c <= avail}):
         torch.set_num_threads(n)
@@ -140,41 +177,44 @@ def cpu_port_setup():
         if best is None or dt < best:
             best, cores = dt, n
     torch.set_num_threads(cores)
-    return O, model, cores
+    return O, model, cores, best
 
 
-def cpu_port_time(O, model, batch, budget_s):
-    """Time the oracle's sample_heun on `batch` images with as many Karras steps as fit the budget; scale to 99 NFE."""
+def cpu_port_time(O, model, wl, batch, budget_s, t_fwd):
+    """Time the oracle's sampler on `batch` images with as many Karras steps as fit the budget; scale to the full NFE."""
+    res, full_nfe = wl["res"], nfe_of(wl["sampler"], wl["steps"])
     g = torch.Generator().manual_seed(123)
-    x = torch.randn(batch, 3, RES, RES, generator=g) * SIGMA_MAX
-    t0 = time.perf_counter()
-    model(x, torch.full([batch], 1.0))
-    t_fwd = time.perf_counter() - t0
-    steps = max(2, min(SAMPLER_STEPS, int((budget_s / max(t_fwd, 1e-3) + 1) // 2)))
+    x = torch.randn(batch, 3, res, res, generator=g) * SIGMA_MAX
+    per_step = 2 if wl["sampler"] == "heun" else 1
+    steps = max(2, min(wl["steps"], int((budget_s / max(t_fwd * batch, 1e-3) + (1 if per_step == 2 else 0)) // per_step)))
     sigmas = O.get_sigmas_karras(steps, SIGMA_MIN, SIGMA_MAX)
     t0 = time.perf_counter()
-    O.sample_heun(model, x, sigmas)
+    oracle_sample(O, model, wl, x, sigmas)
     dt = time.perf_counter() - t0
-    nfe = 2 * steps - 1
-    ips = batch / (dt * NFE / nfe)
-    return ips, f"{batch} image(s) x {nfe} of {NFE} model evaluations (Heun {steps} of {SAMPLER_STEPS} Karras steps) in {dt:.1f} s, scaled by NFE"
+    nfe = nfe_of(wl["sampler"], steps)
+    ips = batch / (dt * full_nfe / nfe)
+    return ips, (f"{batch} image(s) x {nfe} of {full_nfe} model evaluations ({SAMPLER_NAME[wl['sampler']]} {steps} of {wl['steps']} Karras steps) "
+                 f"in {dt:.1f} s, images/s EXTRAPOLATED by the NFE ratio")
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    O, model, cores = cpu_port_setup()
+    wl = args.wl
+    O, model, cores, t_fwd = cpu_port_setup(wl)
     total_budget = 170.0
     per = total_budget / max(1, args.steps + args.warmup)
     vals, sample = [], ""
     for i in range(args.warmup + args.steps):
-        ips, sample = cpu_port_time(O, model, 1, per)
+        ips, sample = cpu_port_time(O, model, wl, 1, per, t_fwd)
         if i >= args.warmup:
             vals.append(ips)
     v = len(vals) / sum(1.0 / a for a in vals)
-    line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1000.0 * PER_GPU_BATCH / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "fp32", "data": "synthetic", "impl": "reference", "config": workload_config(args.gpus, args.batch),
+    line = {"metric": wl["metric"], "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * args.batch / v, "ms_per_step_note": "EXTRAPOLATED: each timed step is a bounded sample (1 image, a shortened "
+            "Karras schedule); images/s is scaled by the NFE ratio and ms_per_step = batch / images/s -- the full workload was not run on the CPU",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp32", "data": "synthetic", "impl": "reference", "config": workload_config(args, args.gpus),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "per step: " + sample + "; CPU torch fp32 port of the reference algorithm (oracle/kdiff_oracle.py); "
                                        "the reference itself is Python and /root/reference does not travel to the GPU box"},
@@ -199,12 +239,14 @@ def main():
     import k_diffusion as K
     from k_diffusion import _native
     S = K.sampling
+    wl = args.wl
+    RES, NFE = wl["res"], nfe_of(wl["sampler"], wl["steps"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    cfg = K.config.load_config(model_config())
+    cfg = K.config.load_config(raw_model_config(wl))
     inner = K.config.make_model(cfg)
     if rank == 0:
         K.synth.synth_init_(inner, seed=1)
@@ -215,8 +257,16 @@ def main():
     lo, hi = K.parallel.shard_range(B * world, rank, world)
     seeds = K.parallel.sample_seeds(123, lo, hi)
     x = K.parallel.init_noise(seeds, (3, RES, RES), SIGMA_MAX, dev)
-    sigmas = S.get_sigmas_karras(SAMPLER_STEPS, SIGMA_MIN, SIGMA_MAX, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def run_sampler(xin, steps=None, x_seeds=seeds):
+        sig = S.get_sigmas_karras(wl["steps"] if steps is None else steps, SIGMA_MIN, SIGMA_MAX, device=dev)
+        if wl["sampler"] == "heun":
+            return S.sample_heun(model, xin, sig, disable=True)
+        if wl["sampler"] == "dpmpp_2m":
+            return S.sample_dpmpp_2m(model, xin, sig, disable=True)
+        ns = S.BrownianTreeNoiseSampler(xin, SIGMA_MIN, SIGMA_MAX, seed=list(x_seeds))      # cfg4: one Brownian path per image
+        return S.sample_euler_ancestral(model, xin, sig, disable=True, noise_sampler=ns)
 
     def barrier():
         if world > 1:
@@ -232,7 +282,7 @@ def main():
 
     def step_device(_):
         flush.zero_()
-        return S.sample_heun(model, x, sigmas, disable=True)
+        return run_sampler(x)
 
     x_host = x.cpu().pin_memory()
     out_host = torch.empty_like(x_host).pin_memory()
@@ -240,7 +290,7 @@ def main():
     def step_e2e(_):
         flush.zero_()
         xd = x_host.to(dev, non_blocking=True)                        # H2D of this step's inputs (pinned)
-        out = S.sample_heun(model, xd, sigmas, disable=True)          # public API call
+        out = run_sampler(xd)                                         # public API call
         out_host.copy_(out, non_blocking=True)                        # D2H of this step's result
         return out
 
@@ -269,16 +319,18 @@ def main():
     value = world * B * args.steps / (ms / 1000.0)
     e2e = world * B * args.steps / (ms_e2e / 1000.0)
 
-    roofline = cpu_baseline = breakdown = None
+    roofline = cpu_baseline = breakdown = parity = None
     if rank == 0 and not args.no_extras:
-        # --- per-kernel-family device times from one eager (non-graph) pass, same batch, 5 Karras steps (9 evaluations)
+        # --- per-kernel device times of one sampler pass with a short schedule (same batch, same kernels): eager launches behind
+        # a gate (kdb_profile_gate) so the host runs ahead and the kernels execute back to back as under graph replay
+        prof_steps = 5 if wl["sampler"] == "heun" else 9
         os.environ["KDB200_CUDA_GRAPH"] = "0"
-        sig5 = S.get_sigmas_karras(5, SIGMA_MIN, SIGMA_MAX, device=dev)
-        S.sample_heun(model, x, sig5, disable=True)
+        run_sampler(x, prof_steps)
         torch.cuda.synchronize()
-        with _native.profile() as prof:
-            S.sample_heun(model, x, sig5, disable=True)
+        with _native.profile(gate_ms=40.0 if RES <= 256 else 120.0) as prof:
+            run_sampler(x, prof_steps)
         os.environ["KDB200_CUDA_GRAPH"] = "1"
+        prof_evals = nfe_of(wl["sampler"], prof_steps)
         total = sum(t for _, t in prof.by_family.values())
         breakdown = {f: {"launches": c, "ms": round(t, 3), "share": round(t / total, 4)} for f, (c, t) in
                      sorted(prof.by_family.items(), key=lambda kv: -kv[1][1])}
@@ -287,12 +339,15 @@ def main():
         gemm_fams = [f for f in prof.by_family if f.startswith("gemm")]
         g_times = [t for f, t in prof.launches if f.startswith("gemm")]
         seq = K.models.flops.linear_layers(cfg["model"], B)
-        per_shape = {}
+        per_shape, per_level = {}, {}
         for idx, t in enumerate(g_times):
             label, M_, N_, K_ = seq[idx % len(seq)]
             key = (label.split(" ", 1)[-1] if " " in label else label.rstrip("0123456789"), M_, N_, K_)
             c, tot = per_shape.get(key, (0, 0.0))
             per_shape[key] = (c + 1, tot + t)
+            lvl = label[:2] if label.startswith("L") else ("mid" if label.startswith("mid") else "merge/split")
+            fl, tt = per_level.get(lvl, (0.0, 0.0))
+            per_level[lvl] = (fl + 2.0 * M_ * N_ * K_, tt + t)
         g_launch, g_ms = len(g_times), sum(g_times)
         flops = 2.0 * K.models.flops.linear_macs(cfg["model"], B) * (len(g_times) / len(seq))
         peaks_file = ROOT / "MEASURED_PEAKS.json"
@@ -302,19 +357,27 @@ def main():
             peak, which = 1400.0, "fallback (B200_PROFILING.md sustained 1.4 PFLOP/s)"
         ach = flops / (g_ms / 1000.0) / 1e12
         shapes = []
-        for (kind, M_, N_, K_), (c, tot) in sorted(per_shape.items(), key=lambda kv: -kv[1][1])[:6]:
+        for (kind, M_, N_, K_), (c, tot) in sorted(per_shape.items(), key=lambda kv: -kv[1][1])[:8]:
             tf = 2.0 * M_ * N_ * K_ * c / (tot / 1000.0) / 1e12
             shapes.append({"op": kind, "M": M_, "N": N_, "K": K_, "launches": c, "avg_launch_us": round(1000.0 * tot / c, 2),
                            "achieved": round(tf, 1), "frac": round(tf / peak, 4), "share_of_step": round(tot / total, 4)})
-        ncu_file = ROOT / "profiles" / "r1_ncu_full_summary.json"
-        traffic, traffic_note = None, "no ncu capture committed"
+        by_level = {lvl: {"achieved": round(fl / (tt / 1000.0) / 1e12, 1), "frac": round(fl / (tt / 1000.0) / 1e12 / peak, 4),
+                          "gemm_ms_per_eval": round(tt / prof_evals, 4)} for lvl, (fl, tt) in sorted(per_level.items())}
+        # attention kernels: algorithmic flops (q k^T and p v) per launch family
+        a_times = [t for f, t in prof.launches if f.startswith("attn")]
+        attn = None
+        if a_times:
+            a_fl = 2.0 * K.models.flops.attention_macs(cfg["model"], B) * prof_evals
+            attn = {"launches": len(a_times), "ms_per_eval": round(sum(a_times) / prof_evals, 4),
+                    "achieved_tflops": round(a_fl / (sum(a_times) / 1000.0) / 1e12, 1), "share_of_step": round(sum(a_times) / total, 4)}
+        ncu_file = ROOT / "profiles" / "r2_ncu_full_summary.json"
+        traffic, traffic_note = None, "no ncu capture committed for this build"
         if ncu_file.exists():
             try:
-                first = next(iter(json.loads(ncu_file.read_text()).values()))[0]
+                first = json.loads(ncu_file.read_text())["roofline_kernel"]
                 traffic = (float(first["dram__bytes_read.sum [Mbyte]"]) + float(first["dram__bytes_write.sum [Mbyte]"])) * 1e6
                 traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the heaviest shape (" + first["launch"] +
-                                "), from the committed ncu --set full capture profiles/r1_ncu_full_summary.json; algorithmic bytes of that "
-                                "launch = A 33.6 MB + W 0.2 MB + out 100.7 MB (the output is written once and mostly still in L2 when the kernel ends)")
+                                "), from the committed ncu --set full capture profiles/r2_ncu_full_summary.json")
             except (KeyError, ValueError, StopIteration):
                 pass
         roofline = {"bound": "tensor", "kernel": "gemm_tc_persist / gemm_tc_kernel (tcgen05 GEMM, all token-stream Linear layers: " +
@@ -322,23 +385,57 @@ def main():
                     "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4), "peak_source": which,
                     "avg_launch_us": round(1000.0 * g_ms / max(g_launch, 1), 2), "launches": g_launch,
                     "share_of_step": round(g_ms / total, 4), "traffic": traffic, "traffic_note": traffic_note, "by_shape": shapes,
-                    "how": "CUDA events after every launch (on the launching stream) of one eager sample_heun with 5 Karras steps at the bench "
-                           "batch; achieved = 2 x Linear MACs of those launches (reference flops.py accounting) / their summed device time",
-                    "note": "K is only 128-1536, so each 128x128 tile carries 0.27-3 us of tensor work but a full fused epilogue (RMSNorm scale, GEGLU / "
-                            "cosine-sim + RoPE / residual, bf16 pack, TMA store); measured per-tile timelines show the epilogue warps' instruction "
-                            "issue, not the tensor pipe or memory, sets the tile period: see DESIGN.md section 4"}
+                    "by_level": by_level, "attention": attn,
+                    "profile_ms_per_eval": round(total / prof_evals, 4), "timed_ms_per_eval": round(ms / args.steps / NFE, 4),
+                    "how": f"CUDA events after every launch (on the launching stream) of one eager {SAMPLER_NAME[wl['sampler']]} with {prof_steps} Karras steps "
+                           "at the bench batch, enqueued behind a gate kernel so no host launch gap falls inside an interval; achieved = 2 x Linear "
+                           "MACs of those launches (reference flops.py accounting) / their summed device time; profile_ms_per_eval is the sum of all "
+                           "intervals per model evaluation (no programmatic-launch overlap between kernels: an event sits between them), "
+                           "timed_ms_per_eval the graph-replayed bench step / NFE"}
+        # --- parity of the benchmarked path (same model object, precision, batch, graph runner) against the fp32 CPU oracle, image 0
+        try:
+            O, o_model = oracle_model(wl, inner)
+            xs = x[:1].cpu()
+            t0c = time.perf_counter()
+            o_model(xs, torch.ones(1))
+            t_f = time.perf_counter() - t0c
+            per_step = 2 if wl["sampler"] == "heun" else 1
+            p_steps = max(2, min(wl["steps"], int(args.parity_seconds / max(t_f, 1e-3) // per_step)))
+            if wl["sampler"] != "euler_ancestral":
+                sig_p = O.get_sigmas_karras(p_steps, SIGMA_MIN, SIGMA_MAX)
+                want = oracle_sample(O, o_model, wl, xs, sig_p)
+                got = run_sampler(x, p_steps)[:1].cpu()
+            else:      # stochastic: feed the oracle the very noise our Brownian tree produces for image 0
+                ns = S.BrownianTreeNoiseSampler(x[:1], SIGMA_MIN, SIGMA_MAX, seed=[seeds[0]])
+                sig_p = O.get_sigmas_karras(p_steps, SIGMA_MIN, SIGMA_MAX)
+                want = O.sample_euler_ancestral(o_model, xs, sig_p, noise_sampler=lambda a, b: ns(float(a), float(b)).cpu())
+                got = run_sampler(x, p_steps)[:1].cpu()
+            d = (got.double() - want.double())
+            budget = None
+            bfile = ROOT / "tests" / "golden" / "bf16_budget.json"
+            if bfile.exists() and args.precision == "bf16":
+                budget = json.loads(bfile.read_text()).get("cfg2_heun10", {}).get("rel_l2")
+            parity = {"rel_l2": float(d.norm() / want.double().norm()), "max_abs": float(d.abs().max()), "ref_rms": float(want.double().pow(2).mean().sqrt()),
+                      "image": 0, "sampler_steps": p_steps, "of_steps": wl["steps"], "vs": "oracle/kdiff_oracle.py fp32 on the CPU, same weights / latent / schedule",
+                      "path": f"{args.precision} token stream, fused RMSNorm, CUDA-graph replay, batch {B} (image 0 compared)",
+                      "reference_own_bf16_rel_l2": budget,
+                      "note": "reference_own_bf16_rel_l2 = distance of the reference under torch.autocast(bf16) from its own fp32 output "
+                              "(cfg2 model, Heun 10 steps; tests/golden/bf16_budget.json) -- the scale of a legitimate bf16 deviation"}
+        except Exception as exc:           # the parity leg must never cost the bench line
+            parity = {"error": repr(exc)}
         if world == 1:
-            O, cpu_model, cores = cpu_port_setup()
-            v, sample = cpu_port_time(O, cpu_model, 2, args.cpu_seconds)
+            O, cpu_model, cores, t_fwd = cpu_port_setup(wl)
+            v, sample = cpu_port_time(O, cpu_model, wl, 2 if RES <= 256 else 1, args.cpu_seconds, t_fwd)
             cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        line = {"metric": wl["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": args.precision, "data": "synthetic", "config": workload_config(world, B),
+                "dtype": args.precision, "data": "synthetic", "config": workload_config(args, world),
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4,
                         "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
+                "parity_rel_l2": None if not parity else parity.get("rel_l2"),
                 "kernel_breakdown": breakdown, "weights_broadcast_bytes": bcast_bytes, "output_finite": finite,
                 "native_library": str(_native.LIB_PATH.relative_to(ROOT))}
         print(json.dumps(line), flush=True)

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define KDB_ABI_VERSION 3
+#define KDB_ABI_VERSION 4
 
 #define KDB_ERR_BAD_ARG      (-1)
 #define KDB_ERR_UNSUPPORTED  (-2)
@@ -47,6 +47,11 @@ int         kdb_launch_breakdown(const char** names, uint64_t* counts, int cap);
  * per launch into the host arrays and returns the number of launches seen. */
 int kdb_profile_begin(int max_launches, void* stream);
 int kdb_profile_end(int* families_host, float* ms_host, int cap);
+/* Holds `stream` busy for `nanoseconds` (one spinning thread, bounded by the GPU's global timer, <= 2 s) so that the host can
+ * enqueue the launches of a profiled region before the first of them runs: the kernels then execute back to back, as they do
+ * under CUDA-graph replay, and the per-launch event intervals contain no host launch gaps.  Measurement aid only: it is not
+ * counted by kdb_launch_count and never used on the product path. */
+int kdb_profile_gate(int64_t nanoseconds, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Solver elementwise ops (HBM-bound, 128-bit vectorised).  n = number of fp32 elements.
@@ -185,6 +190,12 @@ int64_t kdb_model_tap_count(const KdbModel* m);
 
 /* C[M,N] = A[M,K] * W[N,K]^T, bf16 operands, fp32 accumulate in TMEM (tcgen05.mma), bf16 out. */
 int kdb_gemm_bf16(const void* a_bf16, const void* w_bf16, void* c_bf16, int M, int N, int K, void* stream);
+
+/* out[M,N2/2] = value * gelu(gate) of A[M,K] * W_il[N2,K]^T: up_proj with the GEGLU fused in the epilogue
+ * (image_transformer_v2.py:89-95,132-139).  W_il = up_proj.weight with its rows interleaved per 16-row group: 8 value rows
+ * (rows g*8 .. g*8+7 of the first half) followed by the 8 matching gate rows (second half).  ss_in (may be NULL): [M, 8] fp32
+ * sum(x^2) per 128-channel block of A's rows; the epilogue then scales the accumulator by 1/rms (fused RMSNorm). */
+int kdb_gemm_bf16_geglu(const void* a_bf16, const void* w_il_bf16, void* c_bf16, int M, int N2, int K, const float* ss_in, void* stream);
 
 /* out[B,h,w,nh*e] = attention(qkv[B,h,w,3*nh*e]) on fp32 or bf16 token tensors, feature order
  * (t nh e) as produced by qkv_proj (image_transformer_v2.py:377,386,422,431,467). q/k must already be

@@ -339,6 +339,22 @@ int kdb_profile_begin(int max_launches, void* stream) {
   return 0;
 }
 
+__global__ void profile_gate_kernel(unsigned long long ns) {
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  do {
+    __nanosleep(2000);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  } while (t - t0 < ns);
+}
+
+int kdb_profile_gate(int64_t nanoseconds, void* stream) {
+  KDB_REQUIRE(nanoseconds >= 0 && nanoseconds <= 2000000000ll, KDB_ERR_BAD_ARG, "profile_gate: 0 <= nanoseconds <= 2e9");
+  profile_gate_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long)nanoseconds);
+  KDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int kdb_profile_end(int* families_host, float* ms_host, int cap) {
   KDB_REQUIRE(g_prof_on, KDB_ERR_BAD_ARG, "profile_end: not profiling");
   g_prof_on = false;

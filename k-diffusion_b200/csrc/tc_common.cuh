@@ -185,6 +185,16 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return x * fmaf(0.5f, tanh_approx(u), 0.5f);
 }
 
+// fused RMSNorm: sum of the first `parts` (1..8) per-128-channel slots of one row-statistics record.  Exactly `parts` slots are
+// read: the producers write only C / 128 of the 8 slots, the rest of the record is uninitialised workspace.
+__device__ __forceinline__ float rowss_sum(const float4 s0, const float4 s1, const int parts) {
+  const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+  float acc = sv[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) acc += i < parts ? sv[i] : 0.f;
+  return acc;
+}
+
 // ---------------------------------------------------------------- packed fp32 (sm_100 FFMA2 / FMUL2: two lanes per issue slot)
 // The GEMM epilogues are bound by instruction issue, not by the fp32 datapath: pairing neighbouring columns halves the
 // number of multiply / fma instructions.  Results are bit-identical to the scalar .rn operations.

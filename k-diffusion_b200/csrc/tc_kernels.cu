@@ -233,13 +233,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
       if (m < p.M) {
         if (p.ss_in != nullptr) {   // fused out_norm: A is the raw residual stream, W carries the channel scale
           const float4* sp = reinterpret_cast<const float4*>(p.ss_in + m * SS_PARTS);
-          const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
-          const int parts = p.K >> 7;
-          float ssum = s0.x;
-          if (parts > 1) ssum += s0.y;
-          if (parts > 2) ssum += s0.z + s0.w;
-          if (parts > 4) ssum += (s1.x + s1.y) + (s1.z + s1.w);
-          const float rstd = rsqrtf(ssum / (float)p.K + 1e-6f);
+          const float rstd = rsqrtf(tc::rowss_sum(__ldg(sp), __ldg(sp + 1), p.K >> 7) / (float)p.K + 1e-6f);
 #pragma unroll
           for (int i = 0; i < 48; ++i) v[i] *= rstd;
         }
@@ -816,4 +810,12 @@ extern "C" int kdb_gemm_bf16(const void* a, const void* w, void* c, int M, int N
   GemmEpi e;
   KDB_REQUIRE(shape_ok(M, N, K), KDB_ERR_UNSUPPORTED, "gemm_bf16: needs N %% 64 == 0 and K %% 64 == 0 (got M=%d N=%d K=%d)", M, N, K);
   return launch_gemm_tc(static_cast<const bf16*>(a), static_cast<const bf16*>(w), static_cast<bf16*>(c), M, N, K, e, (cudaStream_t)stream);
+}
+
+extern "C" int kdb_gemm_bf16_geglu(const void* a, const void* w_il, void* c, int M, int N2, int K, const float* ss_in, void* stream) {
+  using namespace kdb;
+  KDB_REQUIRE(a && w_il && c, KDB_ERR_BAD_ARG, "gemm_bf16_geglu: NULL operand");
+  KDB_REQUIRE(tc_gemm_geglu_supported(M, N2, K, ss_in != nullptr), KDB_ERR_UNSUPPORTED,
+              "gemm_bf16_geglu: needs N2 %% 128 == 0 and K %% 64 == 0 (K %% 128 == 0, K <= 1024 with ss_in); got M=%d N2=%d K=%d", M, N2, K);
+  return launch_gemm_tc_geglu(static_cast<const bf16*>(a), static_cast<const bf16*>(w_il), static_cast<bf16*>(c), M, N2, K, (cudaStream_t)stream, ss_in);
 }

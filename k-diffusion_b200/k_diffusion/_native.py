@@ -3,7 +3,9 @@
 There is deliberately NO fallback: if the shared library is missing or a tensor is not on a CUDA
 device the call raises.  PyTorch is used only for device memory, streams and views.
 """
+import contextlib
 import ctypes
+import functools
 import os
 from pathlib import Path
 
@@ -15,7 +17,7 @@ LIB_PATH = Path(os.environ.get("KDB200_LIB", _HERE / "_lib" / "libkdb200.so"))
 PREC_FP32, PREC_BF16 = 0, 1
 ATTN_NONE, ATTN_GLOBAL, ATTN_NEIGHBORHOOD, ATTN_SHIFTED_WINDOW = 0, 1, 2, 3
 MAX_LEVELS = 8
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _vp, _i32, _i64, _f32, _f64, _u64, _sz = (ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double,
                                            ctypes.c_uint64, ctypes.c_size_t)
@@ -38,6 +40,7 @@ SIGNATURES = {
     "kdb_launch_breakdown": (_i32, [ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(_u64), _i32]),
     "kdb_profile_begin": (_i32, [_i32, _vp]),
     "kdb_profile_end": (_i32, [ctypes.POINTER(_i32), ctypes.POINTER(_f32), _i32]),
+    "kdb_profile_gate": (_i32, [_i64, _vp]),
     "kdb_solver_euler_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _vp]),
     "kdb_solver_heun_correct": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _vp]),
     "kdb_solver_dpmpp_2m_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _vp]),
@@ -58,6 +61,7 @@ SIGNATURES = {
     "kdb_model_debug_tap": (_i32, [_vp, ctypes.c_char_p, _vp, _i64]),
     "kdb_model_tap_count": (_i64, [_vp]),
     "kdb_gemm_bf16": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "kdb_gemm_bf16_geglu": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "kdb_attention": (_i32, [_i32, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
 }
 
@@ -110,6 +114,30 @@ def stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+_NULL_CTX = contextlib.nullcontext()
+
+
+def device_of(t):
+    """Context that makes `t`'s GPU the current device (kernels launch on the CURRENT device's current stream and the engine
+    allocates there).  A no-op object when it already is -- the common case costs one integer compare."""
+    if t is None or not t.is_cuda or t.device.index == torch.cuda.current_device():
+        return _NULL_CTX
+    return torch.cuda.device(t.device)
+
+
+def _on_device_of_first(fn):
+    """Run a kernel wrapper on the device of its first tensor argument (a list of tensors counts by its first entry)."""
+    @functools.wraps(fn)
+    def wrapper(first, *args, **kwargs):
+        t = first[0] if isinstance(first, (list, tuple)) else first
+        ctx = device_of(t)
+        if ctx is _NULL_CTX:
+            return fn(first, *args, **kwargs)
+        with ctx:
+            return fn(first, *args, **kwargs)
+    return wrapper
+
+
 def f32c(t):
     """fp32 contiguous view/copy (torch plumbing)."""
     if t.dtype != torch.float32:
@@ -130,12 +158,17 @@ def launch_breakdown():
 
 
 class profile:
-    """with profile() as p: ...  -> p.by_family = {family: (launches, total_ms)}, p.launches = [(family, ms)]"""
+    """with profile() as p: ...  -> p.by_family = {family: (launches, total_ms)}, p.launches = [(family, ms)]
 
-    def __init__(self, max_launches=200000):
-        self.cap = max_launches
+    gate_ms > 0 first parks the stream for that long (kdb_profile_gate) so the host can enqueue the region's launches ahead of
+    the GPU: the kernels then run back to back and the event intervals hold no host launch gaps (what a graph replay sees)."""
+
+    def __init__(self, max_launches=200000, gate_ms=0.0):
+        self.cap, self.gate_ms = max_launches, gate_ms
 
     def __enter__(self):
+        if self.gate_ms > 0:
+            check(lib().kdb_profile_gate(int(self.gate_ms * 1e6), stream()))
         check(lib().kdb_profile_begin(self.cap, stream()))
         return self
 
@@ -160,6 +193,7 @@ def _out_like(x, out):
     return torch.empty_like(x) if out is None else out
 
 
+@_on_device_of_first
 def euler_step(x, den, r, noise=None, cn=0.0, out=None):
     """x + (x - den) * r [+ noise * cn]"""
     require_cuda(x, den, noise)
@@ -168,6 +202,7 @@ def euler_step(x, den, r, noise=None, cn=0.0, out=None):
     return out
 
 
+@_on_device_of_first
 def heun_correct(x, den1, x2, den2, a1, a2, out=None):
     """x + (x - den1) * a1 + (x2 - den2) * a2"""
     require_cuda(x, den1, x2, den2)
@@ -176,6 +211,7 @@ def heun_correct(x, den1, x2, den2, a1, a2, out=None):
     return out
 
 
+@_on_device_of_first
 def dpmpp_2m_step(x, den, old_den, a, b, k1, k0, out=None):
     """a x - b (k1 den + k0 old_den)"""
     require_cuda(x, den, old_den)
@@ -184,6 +220,7 @@ def dpmpp_2m_step(x, den, old_den, a, b, k1, k0, out=None):
     return out
 
 
+@_on_device_of_first
 def lincomb(tensors, coefs, out=None):
     """sum_i coefs[i] * tensors[i]   (1..6 fp32 tensors of equal size)"""
     require_cuda(*tensors)
@@ -195,6 +232,7 @@ def lincomb(tensors, coefs, out=None):
     return out
 
 
+@_on_device_of_first
 def to_d(x, den, sigma_b, out=None):
     """(x - den) / sigma[b]"""
     require_cuda(x, den, sigma_b)
@@ -203,6 +241,7 @@ def to_d(x, den, sigma_b, out=None):
     return out
 
 
+@_on_device_of_first
 def precond_scale_in(x, sigma, sigma_data, out=None):
     require_cuda(x, sigma)
     out = _out_like(x, out)
@@ -210,6 +249,7 @@ def precond_scale_in(x, sigma, sigma_data, out=None):
     return out
 
 
+@_on_device_of_first
 def precond_combine(f, x, sigma, sigma_data, out=None):
     require_cuda(f, x, sigma)
     out = _out_like(x, out)
@@ -217,6 +257,7 @@ def precond_combine(f, x, sigma, sigma_data, out=None):
     return out
 
 
+@_on_device_of_first
 def noise_normal(like, seeds, stream_id, out=None):
     require_cuda(like, seeds)
     out = _out_like(like, out)
@@ -224,6 +265,7 @@ def noise_normal(like, seeds, stream_id, out=None):
     return out
 
 
+@_on_device_of_first
 def noise_brownian(like, seeds, t_min, t_max, t0, t1, depth=24, out=None):
     require_cuda(like, seeds)
     out = _out_like(like, out)
@@ -308,8 +350,19 @@ class Engine:
         mapping_cond = None if mapping_cond is None else f32c(mapping_cond)
         class_cond = None if class_cond is None else class_cond.to(torch.int64).contiguous()
         out = torch.empty(rows, self._stride, device=sigma.device, dtype=torch.float32)
-        check(lib().kdb_model_conditioning(self._h, rows, ptr(sigma), ptr(aug_cond), ptr(class_cond), ptr(mapping_cond), ptr(out), stream()))
+        with device_of(sigma):
+            check(lib().kdb_model_conditioning(self._h, rows, ptr(sigma), ptr(aug_cond), ptr(class_cond), ptr(mapping_cond), ptr(out), stream()))
         return out
+
+    def check_class_range(self, class_cond):
+        """nn.Embedding raises on an out-of-range index (reference image_transformer_v2.py:735); the conditioning kernel indexes
+        class_emb with it, so validate on the host (one device->host sync; callers do it once per sampler call, not per step)."""
+        n = int(self.cfg.num_classes)
+        if class_cond is None or n <= 0:
+            return
+        lo, hi = int(class_cond.min()), int(class_cond.max())
+        if lo < 0 or hi >= n:
+            raise IndexError(f"class_cond values must lie in [0, {n}) (class_emb has {n} rows), got [{lo}, {hi}]")
 
     def _workspace(self, precision, B, H, W, device):
         need = int(lib().kdb_model_workspace_bytes(self._h, precision, B, H, W))
@@ -324,8 +377,9 @@ class Engine:
         if out is None:
             out = torch.empty(B, self.cfg.out_channels, H, W, device=x.device, dtype=torch.float32)
         ws = self._workspace(precision, B, H, W, x.device)
-        check(lib().kdb_model_forward(self._h, precision, B, H, W, ptr(x), ptr(sigma), float(sigma_data), ptr(cond), cond_batch_stride,
-                                      ptr(out), ptr(ws), ws.numel(), stream()))
+        with device_of(x):
+            check(lib().kdb_model_forward(self._h, precision, B, H, W, ptr(x), ptr(sigma), float(sigma_data), ptr(cond), cond_batch_stride,
+                                          ptr(out), ptr(ws), ws.numel(), stream()))
         return out
 
     def arm_tap(self, name, capacity, device):
@@ -341,6 +395,7 @@ class Engine:
 # stand-alone kernels (unit tests / profiling)
 # ---------------------------------------------------------------------------------------------
 
+@_on_device_of_first
 def gemm_bf16(a, w):
     """a [M,K] bf16, w [N,K] bf16 -> [M,N] bf16 on the tcgen05 kernel (N % 64 == 0, K % 64 == 0)."""
     require_cuda(a, w)
@@ -352,6 +407,28 @@ def gemm_bf16(a, w):
     return out
 
 
+def interleave_geglu_rows(w_up):
+    """up_proj.weight [2F, K] -> the value/gate row interleave the fused GEGLU epilogue expects (8 value rows, 8 gate rows)."""
+    F2, K = w_up.shape
+    F = F2 // 2
+    val, gate = w_up[:F].reshape(F // 8, 8, K), w_up[F:].reshape(F // 8, 8, K)
+    return torch.cat([val, gate], dim=1).reshape(F2, K).contiguous()
+
+
+@_on_device_of_first
+def gemm_bf16_geglu(a, w_up, ss_in=None):
+    """a [M,K] bf16, w_up [2F,K] bf16 (reference row order) -> value * gelu(gate) [M,F] bf16 on the persistent tcgen05 kernel."""
+    require_cuda(a, w_up, ss_in)
+    assert a.dtype == torch.bfloat16 and w_up.dtype == torch.bfloat16 and a.is_contiguous()
+    M, K = a.shape
+    N2 = w_up.shape[0]
+    w_il = interleave_geglu_rows(w_up)
+    out = torch.empty(M, N2 // 2, dtype=torch.bfloat16, device=a.device)
+    check(lib().kdb_gemm_bf16_geglu(ptr(a), ptr(w_il), ptr(out), M, N2, K, ptr(ss_in), stream()))
+    return out
+
+
+@_on_device_of_first
 def attention(qkv, h, w, n_heads, d_head, attn_type, attn_param=0, shift=0, fast=False):
     """qkv [B, h*w, 3*n_heads*d_head] (fp32 or bf16, q/k already normalised + rotated) -> [B, h*w, n_heads*d_head]."""
     require_cuda(qkv)

@@ -239,6 +239,8 @@ class ImageTransformerDenoiserModelV2(nn.Module):
             if sig.shape != (x.shape[0],):
                 raise ValueError(f"sigma must have shape [{x.shape[0]}], got {tuple(sigma.shape)}")
             eng = self.engine()
+            if self.class_emb is not None and not torch.cuda.is_current_stream_capturing():
+                eng.check_class_range(class_cond)           # nn.Embedding raises on out-of-range labels (reference :735)
             cond = eng.conditioning(sig, aug_cond, class_cond if self.class_emb is not None else None,
                                     mapping_cond if self.mapping_cond_in_proj is not None else None)
             res = eng.forward(xin, sig, cond, eng.cond_stride, sigma_data, self.resolved_precision(), out=out)

@@ -15,6 +15,7 @@ How this differs from the reference implementation:
   * `sample_euler` / `sample_heun` only draw churn noise when gamma > 0 (the reference draws and
     discards `randn_like(x)` every step; samples are identical, the global RNG offset afterwards is not).
 """
+import functools
 import math
 import os
 
@@ -446,8 +447,14 @@ class _Evaluator:
         self.sigma_rows = sig[:, None].expand(len(eval_sigmas), self.B).contiguous()
         if self.native:
             inner = model.inner_model
+            if x.ndim != 4:
+                raise ValueError(f"expected x of shape [B, C, H, W], got {tuple(x.shape)}")
+            if inner.training and any(s.dropout > 0 for s in inner.levels):       # same checks as the module's own forward
+                raise RuntimeError("dropout > 0 in training mode: the native path is inference only -- call model.eval()")
             inner._check_cond(extra_args.get("class_cond"), extra_args.get("mapping_cond"))
             self.inner, self.eng = inner, inner.engine()
+            if inner.class_emb is not None and not torch.cuda.is_current_stream_capturing():
+                self.eng.check_class_range(extra_args.get("class_cond"))          # once per sampler call, outside the loop
             self.precision = inner.resolved_precision()
             self.sigma_data = float(model.sigma_data)
             self.per_sample = any(extra_args.get(k) is not None for k in _NATIVE_KW)
@@ -456,11 +463,17 @@ class _Evaluator:
     def capturable(self):
         return self.native
 
+    def static_args(self):
+        """The per-sample conditioning tensors a captured graph reads ((name, tensor) pairs, stable order)."""
+        return [(k, self.extra_args[k]) for k in sorted(_NATIVE_KW) if self.native and self.extra_args.get(k) is not None]
+
     def __call__(self, k, x, out=None):
         if not self.native:
             return self.model(x, self.sigma_rows[k], **self.extra_args)
         if self.per_sample:
-            cond = self.inner.conditioning(self.sigma_rows[k], **self.extra_args)
+            cond = self.eng.conditioning(self.sigma_rows[k], self.extra_args.get("aug_cond"),
+                                         self.extra_args.get("class_cond") if self.inner.class_emb is not None else None,
+                                         self.extra_args.get("mapping_cond") if self.inner.mapping_cond_in_proj is not None else None)
             stride = self.eng.cond_stride
         else:
             if self.table is None:          # one launch for every evaluation of the schedule (a cached graph never needs it)
@@ -484,6 +497,7 @@ def _scalar_like(sigmas, v):
 
 
 _graph_cache = {}
+_GLOBAL_RNG = object()          # marker: the body draws from torch's global generator -> never captured
 
 
 def _progress(plan, disable):
@@ -497,43 +511,85 @@ def _progress(plan, disable):
 _progress.quiet = False
 
 
-def _graph_key(name, ev, x, sig, params):
-    return (name, id(ev.inner), ev.eng._sig, tuple(x.shape), x.device.index, tuple(sig), ev.precision, params)
+def _noise_kind(noise_sampler):
+    """How a noise sampler may be used inside a captured graph.
+
+    'none'      no noise is drawn
+    'brownian'  BrownianTreeNoiseSampler: a pure function of (seeds, sigma, sigma_next) -> capturable; the seeds live in a
+                static device buffer owned by the cache entry and are refreshed before every replay, so one graph serves
+                every seed (and a sampler that was freed can never be replayed by address)
+    'foreign'   anything else (global-RNG randn, PhiloxNoiseSampler's call counter, user callables): eager only
+    """
+    if noise_sampler is None:
+        return 'none'
+    if isinstance(noise_sampler, BrownianTreeNoiseSampler):
+        return 'brownian'
+    return 'foreign'
 
 
-def _run(name, body, ev, x, sig, params, callback, noise_capturable=True):
+def _graph_key(name, ev, x, sig, params, noise_sampler):
+    key = (name, id(ev.inner), ev.eng._sig, ev.sigma_data, tuple(x.shape), x.device.index, tuple(sig), ev.precision, params,
+           tuple((k, tuple(t.shape), str(t.dtype)) for k, t in ev.static_args()))
+    if _noise_kind(noise_sampler) == 'brownian':
+        tr = noise_sampler.tree          # the entry keeps `transform` alive, so its id cannot be recycled while the key exists
+        key += (('brownian', tr.t0, tr.t1, tr.sign, tr.depth, tr.batched, int(tr.seeds.numel()), id(noise_sampler.transform)),)
+    return key
+
+
+class _GraphEntry:
+    """One captured sampler call.  Holds every object whose ADDRESS the graph (or its key) depends on."""
+    __slots__ = ("graph", "static_in", "static_out", "kernels", "ev", "ws", "static_args", "static_seeds", "transform")
+
+
+def _run(name, body, ev, x, sig, params, callback, noise_sampler=None):
     """Run `body(x) -> x_out` eagerly, or as a cached CUDA graph when everything inside is ours."""
-    use_graph = (os.environ.get(_GRAPH_ENV, "1") != "0" and callback is None and ev.capturable() and not ev.per_sample
-                 and noise_capturable and not torch.cuda.is_current_stream_capturing())
+    kind = _noise_kind(noise_sampler)
+    use_graph = (os.environ.get(_GRAPH_ENV, "1") != "0" and callback is None and ev.capturable() and kind != 'foreign'
+                 and not torch.cuda.is_current_stream_capturing())
     if not use_graph:
         return body(x)
-    key = _graph_key(name, ev, x, sig, params)
+    key = _graph_key(name, ev, x, sig, params, noise_sampler)
     entry = _graph_cache.get(key)
     if entry is None:
-        static_in = torch.empty_like(x)
-        static_in.copy_(x)
+        entry = _GraphEntry()
+        entry.static_in = torch.empty_like(x)
+        entry.static_in.copy_(x)
+        # per-sample conditioning tensors and Brownian seeds are read through static copies owned by the entry
+        entry.static_args = {k: t.clone() for k, t in ev.static_args()}
+        entry.static_seeds = noise_sampler.tree.seeds.clone() if kind == 'brownian' else None
+        entry.transform = noise_sampler.transform if kind == 'brownian' else None
+        call_args, ev.extra_args = ev.extra_args, {**ev.extra_args, **entry.static_args}
+        if kind == 'brownian':
+            call_seeds, noise_sampler.tree.seeds = noise_sampler.tree.seeds, entry.static_seeds
         side = torch.cuda.Stream(device=x.device)
         side.wait_stream(torch.cuda.current_stream())
         _progress.quiet = True
         try:
             with torch.cuda.stream(side):                  # warm-up outside capture (allocations, pos tables)
-                body(static_in)
+                body(entry.static_in)
             torch.cuda.current_stream().wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
+            entry.graph = torch.cuda.CUDAGraph()
             n0 = _native.launch_count()
-            with torch.cuda.graph(graph):
-                static_out = body(static_in)
-            kernels = _native.launch_count() - n0              # kernel nodes of ours inside the graph
+            with torch.cuda.graph(entry.graph):
+                entry.static_out = body(entry.static_in)
+            entry.kernels = _native.launch_count() - n0        # kernel nodes of ours inside the graph
         finally:
             _progress.quiet = False
+            ev.extra_args = call_args
+            if kind == 'brownian':
+                noise_sampler.tree.seeds = call_seeds
+        entry.ev, entry.ws = ev, ev.eng._ws                    # keeps the model, its engine and the workspace alive
         if len(_graph_cache) >= int(os.environ.get("KDB200_GRAPH_CACHE", "8")):
             _graph_cache.pop(next(iter(_graph_cache)))
-        entry = _graph_cache[key] = (graph, static_in, static_out, kernels, ev, ev.eng._ws)
-    graph, static_in, static_out, kernels = entry[:4]
-    static_in.copy_(x)
-    graph.replay()
-    _replayed[0] += kernels
-    return static_out.clone()
+        _graph_cache[key] = entry
+    entry.static_in.copy_(x)
+    for k, t in ev.static_args():
+        entry.static_args[k].copy_(t)
+    if kind == 'brownian':
+        entry.static_seeds.copy_(noise_sampler.tree.seeds)
+    entry.graph.replay()
+    _replayed[0] += entry.kernels
+    return entry.static_out.clone()
 
 
 _replayed = [0]
@@ -552,6 +608,17 @@ def clear_graph_cache():
 # samplers
 # --------------------------------------------------------------------------------------------
 
+def _on_x_device(fn):
+    """Run a sampler with x's GPU as the current device: kernels launch on the current device's current stream and the engine
+    allocates its tables there, so `x` on cuda:1 under current device cuda:0 must switch (the reference's ATen ops do)."""
+    @functools.wraps(fn)
+    def wrapper(model, x, *args, **kwargs):
+        with _native.device_of(x):
+            return fn(model, x, *args, **kwargs)
+    return wrapper
+
+
+@_on_x_device
 @torch.no_grad()
 def sample_euler(model, x, sigmas, extra_args=None, callback=None, disable=None, s_churn=0., s_tmin=0., s_tmax=float('inf'), s_noise=1.):
     """Algorithm 2 (Euler steps) from Karras et al. (2022)."""
@@ -569,16 +636,16 @@ def sample_euler(model, x, sigmas, extra_args=None, callback=None, disable=None,
             xc = _native.euler_step(xc, den, st['r'])
         return xc
 
-    out = _run('euler', body, ev, xw, sig, (s_churn, s_tmin, s_tmax, s_noise), callback, noise_capturable=s_churn == 0)
+    out = _run('euler', body, ev, xw, sig, (s_churn, s_tmin, s_tmax, s_noise), callback, noise_sampler=_GLOBAL_RNG if any(st['gamma'] > 0 for st in plan) else None)
     return _finish(out, x)
 
 
+@_on_x_device
 @torch.no_grad()
 def sample_euler_ancestral(model, x, sigmas, extra_args=None, callback=None, disable=None, eta=1., s_noise=1., noise_sampler=None):
     """Ancestral sampling with Euler method steps."""
     xw, sig, extra_args = _prepare(x, sigmas, extra_args)
     ours = isinstance(noise_sampler, (BrownianTreeNoiseSampler, PhiloxNoiseSampler))
-    stateless = isinstance(noise_sampler, BrownianTreeNoiseSampler)
     noise_sampler = default_noise_sampler(xw) if noise_sampler is None else noise_sampler
     plan = plan_euler_ancestral(sig, eta, s_noise)
     ev = _Evaluator(model, xw, extra_args, [s for st in plan for s in st['evals']])
@@ -595,11 +662,12 @@ def sample_euler_ancestral(model, x, sigmas, extra_args=None, callback=None, dis
             xc = _native.euler_step(xc, den, st['r'], noise=noise, cn=st['cn'])
         return xc
 
-    # a graph replays the same noise every call: only legal for the Brownian tree (a pure function of sigma)
-    out = _run('euler_a', body, ev, xw, sig, (eta, s_noise, id(noise_sampler)), callback, noise_capturable=ours and stateless)
+    # a graph replays the same noise kernels every call: only legal for the Brownian tree (a pure function of seeds and sigma)
+    out = _run('euler_a', body, ev, xw, sig, (eta, s_noise), callback, noise_sampler=noise_sampler if any(st['noise'] for st in plan) else None)
     return _finish(out, x)
 
 
+@_on_x_device
 @torch.no_grad()
 def sample_heun(model, x, sigmas, extra_args=None, callback=None, disable=None, s_churn=0., s_tmin=0., s_tmax=float('inf'), s_noise=1.):
     """Algorithm 2 (Heun steps) from Karras et al. (2022)."""
@@ -625,10 +693,11 @@ def sample_heun(model, x, sigmas, extra_args=None, callback=None, disable=None, 
                 xc = _native.heun_correct(xc, den, x_2, den_2, st['a1'], st['a2'])      # trapezoidal corrector
         return xc
 
-    out = _run('heun', body, ev, xw, sig, (s_churn, s_tmin, s_tmax, s_noise), callback, noise_capturable=s_churn == 0)
+    out = _run('heun', body, ev, xw, sig, (s_churn, s_tmin, s_tmax, s_noise), callback, noise_sampler=_GLOBAL_RNG if any(st['gamma'] > 0 for st in plan) else None)
     return _finish(out, x)
 
 
+@_on_x_device
 @torch.no_grad()
 def sample_dpmpp_2m(model, x, sigmas, extra_args=None, callback=None, disable=None):
     """DPM-Solver++(2M)."""
@@ -661,7 +730,6 @@ def _sample_ops(name, model, x, sigmas, plan_fn, extra_args, callback, disable, 
     plan = plan_fn(sig)
     needs_noise = any(op[0] == 'noise' for st in plan for op in st['ops'])
     ours = isinstance(noise_sampler, (BrownianTreeNoiseSampler, PhiloxNoiseSampler))
-    stateless = isinstance(noise_sampler, BrownianTreeNoiseSampler)
     churned = any(st.get('gamma', 0) > 0 for st in plan)
     ev = _Evaluator(model, xw, extra_args, [s_ for st in plan for s_ in st['evals']])
 
@@ -690,9 +758,8 @@ def _sample_ops(name, model, x, sigmas, plan_fn, extra_args, callback, disable, 
                     T[op[1]] = T[op[2]]
         return T['x']
 
-    # a graph replays the same noise every call: only legal without noise or with the Brownian tree (a pure function of sigma)
-    capturable = (not needs_noise or (ours and stateless)) and not churned
-    out = _run(name, body, ev, xw, sig, params + ((id(noise_sampler),) if needs_noise else ()), callback, noise_capturable=capturable)
+    # a graph replays the same noise kernels every call: only legal without noise or with the Brownian tree
+    out = _run(name, body, ev, xw, sig, params, callback, noise_sampler=_GLOBAL_RNG if churned else (noise_sampler if needs_noise else None))
     return _finish(out, x)
 
 
@@ -701,6 +768,7 @@ def _default_brownian(x, sigmas):
     return BrownianTreeNoiseSampler(_native.f32c(x), sigma_min, sigma_max)
 
 
+@_on_x_device
 @torch.no_grad()
 def sample_dpm_2(model, x, sigmas, extra_args=None, callback=None, disable=None, s_churn=0., s_tmin=0., s_tmax=float('inf'), s_noise=1.):
     """A sampler inspired by DPM-Solver-2 and Algorithm 2 from Karras et al. (2022)  (reference sampling.py:187-214)."""
@@ -708,6 +776,7 @@ def sample_dpm_2(model, x, sigmas, extra_args=None, callback=None, disable=None,
                        (s_churn, s_tmin, s_tmax, s_noise), churn_noise=s_noise)
 
 
+@_on_x_device
 @torch.no_grad()
 def sample_dpm_2_ancestral(model, x, sigmas, extra_args=None, callback=None, disable=None, eta=1., s_noise=1., noise_sampler=None):
     """Ancestral sampling with DPM-Solver second-order steps  (reference sampling.py:217-244)."""
@@ -716,12 +785,14 @@ def sample_dpm_2_ancestral(model, x, sigmas, extra_args=None, callback=None, dis
                        (eta, s_noise), noise_sampler)
 
 
+@_on_x_device
 @torch.no_grad()
 def sample_lms(model, x, sigmas, extra_args=None, callback=None, disable=None, order=4):
     """Linear multistep (Adams-Bashforth in sigma)  (reference sampling.py:247-277)."""
     return _sample_ops('lms', model, x, sigmas, lambda sig: plan_lms(sig, order), extra_args, callback, disable, (order,))
 
 
+@_on_x_device
 @torch.no_grad()
 def sample_dpmpp_2s_ancestral(model, x, sigmas, extra_args=None, callback=None, disable=None, eta=1., s_noise=1., noise_sampler=None):
     """Ancestral sampling with DPM-Solver++(2S) second-order steps  (reference sampling.py:508-539)."""
@@ -730,6 +801,7 @@ def sample_dpmpp_2s_ancestral(model, x, sigmas, extra_args=None, callback=None, 
                        (eta, s_noise), noise_sampler)
 
 
+@_on_x_device
 @torch.no_grad()
 def sample_dpmpp_sde(model, x, sigmas, extra_args=None, callback=None, disable=None, eta=1., s_noise=1., noise_sampler=None, r=1 / 2):
     """DPM-Solver++ (stochastic)  (reference sampling.py:542-581)."""
@@ -738,6 +810,7 @@ def sample_dpmpp_sde(model, x, sigmas, extra_args=None, callback=None, disable=N
                        (eta, s_noise, r), noise_sampler)
 
 
+@_on_x_device
 @torch.no_grad()
 def sample_dpmpp_2m_sde(model, x, sigmas, extra_args=None, callback=None, disable=None, eta=1., s_noise=1., noise_sampler=None,
                         solver_type='midpoint'):
@@ -749,6 +822,7 @@ def sample_dpmpp_2m_sde(model, x, sigmas, extra_args=None, callback=None, disabl
                        disable, (eta, s_noise, solver_type), noise_sampler)
 
 
+@_on_x_device
 @torch.no_grad()
 def sample_dpmpp_3m_sde(model, x, sigmas, extra_args=None, callback=None, disable=None, eta=1., s_noise=1., noise_sampler=None):
     """DPM-Solver++(3M) SDE  (reference sampling.py:655-703)."""

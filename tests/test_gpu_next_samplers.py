@@ -1,0 +1,145 @@
+"""SURVEY 8(f) row 1 on the GPU: the seven remaining fixed-schedule samplers (sample_dpm_2, sample_dpm_2_ancestral, sample_lms,
+sample_dpmpp_2s_ancestral, sample_dpmpp_sde, sample_dpmpp_2m_sde, sample_dpmpp_3m_sde).
+
+Their oracle restatements are pinned against the reference and their host plans / executor are verified on the CPU
+(tests/test_oracle_golden.py, tests/test_host_logic.py).  Here the CUDA path runs (a) all 14 trajectories recorded from the
+real reference (oracle/make_golden_next.py) around an opaque model, (b) every entry point on the native cfg1 model against the
+CPU oracle at the north-star tolerance, (c) the CUDA-graph cache rules for noise samplers.
+"""
+import pytest
+import torch
+
+import k_diffusion as K
+from conftest import assert_close, load_npz
+from oracle import kdiff_oracle as O
+from test_gpu_parity import build
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+S = K.sampling
+DEV = "cuda"
+toy2 = lambda x, s, **kw: x / (1 + s[:, None, None, None] ** 2) + 0.1 * torch.tanh(x)
+
+# name in the fixture -> (entry point, kwargs, draws noise)
+TRAJECTORIES = {
+    "sample_dpm_2": ("sample_dpm_2", {}, False),
+    "sample_lms": ("sample_lms", {}, False),
+    "sample_lms_order2": ("sample_lms", dict(order=2), False),
+    "sample_dpm_2_ancestral": ("sample_dpm_2_ancestral", {}, True),
+    "sample_dpm_2_ancestral_eta05": ("sample_dpm_2_ancestral", dict(eta=0.5, s_noise=0.9), True),
+    "sample_dpmpp_2s_ancestral": ("sample_dpmpp_2s_ancestral", {}, True),
+    "sample_dpmpp_2s_ancestral_eta0": ("sample_dpmpp_2s_ancestral", dict(eta=0.), True),
+    "sample_dpmpp_sde": ("sample_dpmpp_sde", {}, True),
+    "sample_dpmpp_sde_r03": ("sample_dpmpp_sde", dict(eta=0.7, s_noise=0.9, r=0.3), True),
+    "sample_dpmpp_2m_sde": ("sample_dpmpp_2m_sde", {}, True),
+    "sample_dpmpp_2m_sde_heun": ("sample_dpmpp_2m_sde", dict(eta=0.6, solver_type="heun"), True),
+    "sample_dpmpp_2m_sde_eta0": ("sample_dpmpp_2m_sde", dict(eta=0.), True),
+    "sample_dpmpp_3m_sde": ("sample_dpmpp_3m_sde", {}, True),
+    "sample_dpmpp_3m_sde_eta05": ("sample_dpmpp_3m_sde", dict(eta=0.5, s_noise=0.8), True),
+}
+
+
+@pytest.mark.parametrize("key", sorted(TRAJECTORIES))
+def test_opaque_model_next_samplers_vs_reference_trajectories(key):
+    z = load_npz("toy_next_samplers.npz")
+    x, sig, nz = z["x"].to(DEV), z["sigmas"].to(DEV), z["noise"].to(DEV)
+    fn, kw, noisy = TRAJECTORIES[key]
+    if noisy:
+        it = iter(nz)
+        kw = dict(kw, noise_sampler=lambda a, b: next(it))
+    assert_close(getattr(S, fn)(toy2, x, sig, disable=True, **kw), z[key], rtol=1e-4, atol=2e-5, what=key)
+
+
+def test_native_model_next_samplers_vs_oracle():
+    """cfg1 (MNIST transformer, class-conditional, fp32 exact path): CUDA path against the CPU oracle on the same inputs,
+    rtol 1e-3 / atol 1e-5, all seven entry points."""
+    cfg, sd, inner, model, z = build("cfg1_mnist")
+    x, sigmas = z["x"].to(DEV), z["sigmas"].to(DEV)
+    cc = z["class_cond"]
+    ea = dict(class_cond=cc.to(DEV))
+    oracle_model = O.make_denoiser(sd, cfg["model"])
+    om = lambda xx, ss, **kw: oracle_model(xx, ss, class_cond=cc)
+    noise = z["noise"]
+
+    def pair():
+        it_g, it_o = iter(noise.to(DEV)), iter(noise)
+        return (lambda a, b: next(it_g)), (lambda a, b: next(it_o))
+
+    assert_close(S.sample_dpm_2(model, x, sigmas, extra_args=ea, disable=True), O.sample_dpm_2(om, z["x"], z["sigmas"]), what="dpm_2")
+    assert_close(S.sample_lms(model, x, sigmas, extra_args=ea, disable=True), O.sample_lms(om, z["x"], z["sigmas"]), what="lms")
+    for name in ("sample_dpmpp_2m_sde", "sample_dpmpp_3m_sde"):
+        ng, no = pair()
+        got = getattr(S, name)(model, x, sigmas, extra_args=ea, disable=True, noise_sampler=ng)
+        assert_close(got, getattr(O, name)(om, z["x"], z["sigmas"], noise_sampler=no), what=name)
+    # two noise draws per step: the fixture records 10 tensors -> 5 Karras steps
+    sig5 = K.sampling.get_sigmas_karras(5, 1e-2, 80)
+    for name in ("sample_dpm_2_ancestral", "sample_dpmpp_2s_ancestral", "sample_dpmpp_sde"):
+        ng, no = pair()
+        got = getattr(S, name)(model, x, sig5.to(DEV), extra_args=ea, disable=True, noise_sampler=ng)
+        assert_close(got, getattr(O, name)(om, z["x"], sig5, noise_sampler=no), what=name)
+
+
+def test_brownian_default_graph_equals_eager(monkeypatch):
+    """Unconditional native model + an explicit Brownian-tree noise sampler: the captured graph must replay the eager launches."""
+    cfg, sd, inner, model, z = build("sw64")
+    x, sigmas = z["x"].to(DEV), z["sigmas"].to(DEV)
+    ns = S.BrownianTreeNoiseSampler(x, float(sigmas[sigmas > 0].min()), float(sigmas.max()), seed=list(range(x.shape[0])))
+    S.clear_graph_cache()
+    g1 = S.sample_dpmpp_2m_sde(model, x, sigmas, disable=True, noise_sampler=ns)
+    monkeypatch.setenv("KDB200_CUDA_GRAPH", "0")
+    e1 = S.sample_dpmpp_2m_sde(model, x, sigmas, disable=True, noise_sampler=ns)
+    assert torch.isfinite(g1).all() and torch.equal(g1, e1)
+
+
+def test_graph_cache_is_keyed_on_noise_content_not_object_identity(monkeypatch):
+    """a graph must never replay a freed sampler's seeds.  Back-to-back default samplers (fresh random seed,
+    freed on return, CPython reuses the address) must differ; two samplers with the same explicit seeds must agree; a new seed
+    list must give the eager result for THAT list."""
+    cfg, sd, inner, model, z = build("sw64")
+    x, sigmas = z["x"].to(DEV), z["sigmas"].to(DEV)
+    B = x.shape[0]
+    lo, hi = float(sigmas[sigmas > 0].min()), float(sigmas.max())
+    S.clear_graph_cache()
+    torch.manual_seed(0)
+    a = S.sample_dpmpp_2m_sde(model, x, sigmas, disable=True)
+    b = S.sample_dpmpp_2m_sde(model, x, sigmas, disable=True)
+    assert not torch.equal(a, b), "two default (random-seed) Brownian samplers replayed the same noise"
+    mk = lambda seeds: S.BrownianTreeNoiseSampler(x, lo, hi, seed=seeds)
+    s1 = S.sample_euler_ancestral(model, x, sigmas, disable=True, noise_sampler=mk(list(range(10, 10 + B))))
+    s2 = S.sample_euler_ancestral(model, x, sigmas, disable=True, noise_sampler=mk(list(range(10, 10 + B))))
+    s3 = S.sample_euler_ancestral(model, x, sigmas, disable=True, noise_sampler=mk(list(range(50, 50 + B))))
+    assert torch.equal(s1, s2) and not torch.equal(s1, s3)
+    monkeypatch.setenv("KDB200_CUDA_GRAPH", "0")
+    e3 = S.sample_euler_ancestral(model, x, sigmas, disable=True, noise_sampler=mk(list(range(50, 50 + B))))
+    assert torch.equal(s3, e3)
+
+
+def test_graph_cache_is_keyed_on_sigma_data():
+    """sigma_data is baked into the captured patch-in / patch-out kernels."""
+    cfg, sd, inner, model, z = build("sw64")
+    x, sigmas = z["x"].to(DEV), z["sigmas"].to(DEV)
+    S.clear_graph_cache()
+    a = S.sample_heun(model, x, sigmas, disable=True)
+    other = K.Denoiser(inner, sigma_data=float(model.sigma_data) * 2)
+    b = S.sample_heun(other, x, sigmas, disable=True)
+    assert not torch.equal(a, b)
+    want = O.sample_heun(O.make_denoiser(sd, dict(cfg["model"], sigma_data=float(model.sigma_data) * 2)), z["x"], z["sigmas"])
+    assert_close(b, want, what="heun with the second Denoiser's sigma_data")
+
+
+def test_class_conditional_graph_equals_eager(monkeypatch):
+    """Per-sample conditioning (class labels) is captured too: the graph reads static copies of the extra_args tensors that are
+    refreshed before every replay.  cfg1, fp32 exact path: graph == eager bit for bit, and new labels give new results."""
+    cfg, sd, inner, model, z = build("cfg1_mnist")
+    x, sigmas = z["x"].to(DEV), z["sigmas"].to(DEV)
+    cc = z["class_cond"].to(DEV)
+    S.clear_graph_cache()
+    g1 = S.sample_heun(model, x, sigmas, extra_args=dict(class_cond=cc), disable=True)
+    assert_close(g1, z["heun"], what="heun (class-conditional graph)")
+    cc2 = torch.tensor([5, 5, 0, 9], device=DEV)
+    g2 = S.sample_heun(model, x, sigmas, extra_args=dict(class_cond=cc2), disable=True)          # replay with refreshed labels
+    monkeypatch.setenv("KDB200_CUDA_GRAPH", "0")
+    e1 = S.sample_heun(model, x, sigmas, extra_args=dict(class_cond=cc), disable=True)
+    e2 = S.sample_heun(model, x, sigmas, extra_args=dict(class_cond=cc2), disable=True)
+    assert torch.equal(g1, e1) and torch.equal(g2, e2) and not torch.equal(g1, g2)
+    with pytest.raises(IndexError, match="class_cond"):
+        S.sample_heun(model, x, sigmas, extra_args=dict(class_cond=torch.tensor([0, 1, 2, 11], device=DEV)), disable=True)

@@ -2,7 +2,11 @@
 """Per-launch device times of ONE denoiser evaluation (eager launches, CUDA events after every kernel),
 annotated with the GEMM shape each tensor-core launch corresponds to.  Run on the GPU box:
 
-    python tools/profile_forward.py [--batch 32] [--precision bf16] [--json out.json]
+    python tools/profile_forward.py [--batch 32] [--precision bf16] [--json out.json] [--per-sample]
+
+Default route = what the samplers (and bench.py) run: ONE shared conditioning row per evaluation, AdaRMSNorm folded into the
+GEMMs (fold kernel + row statistics), launches enqueued behind a gate kernel so they execute back to back like a graph replay.
+--per-sample profiles the route `model(x, sigma)` takes (per-sample conditioning rows, stand-alone RMSNorm kernels).
 """
 import argparse
 import json
@@ -54,6 +58,8 @@ def main():
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--json", default=None)
     ap.add_argument("--config", default="sw", choices=["sw", "na"], help="sw = cfg2 shifted-window model, na = cfg3/4 neighbourhood model")
+    ap.add_argument("--per-sample", action="store_true")
+    ap.add_argument("--repeat", type=int, default=1, help="evaluations inside the profiled region")
     args = ap.parse_args()
     fixture = "cfg2_sw256_shapes.json" if args.config == "sw" else "cfg3_na256_config.json"
     cfg = K.config.load_config(json.loads((ROOT / "tests/golden" / fixture).read_text())["config"])
@@ -61,30 +67,40 @@ def main():
     model = K.Denoiser(inner, sigma_data=cfg["model"]["sigma_data"])
     x = torch.randn(args.batch, 3, 256, 256, device="cuda") * 10
     sig = torch.full([args.batch], 3.0, device="cuda")
+    eng = inner.engine()
+    table = eng.conditioning(sig[:1])
+
+    def evaluate():
+        if args.per_sample:
+            return model(x, sig)
+        return eng.forward(x, sig, table[0], 0, float(model.sigma_data), inner.resolved_precision())
+
     for _ in range(3):
-        model(x, sig)
+        evaluate()
     torch.cuda.synchronize()
-    with _native.profile() as prof:
-        model(x, sig)
+    with _native.profile(gate_ms=10.0 * args.repeat) as prof:
+        for _ in range(args.repeat):
+            evaluate()
     seq = gemm_sequence(cfg["model"], args.batch)
     gi = 0
     rows = []
     peak = 1396.9
     for fam, ms in prof.launches:
         note = ""
-        if fam.startswith("gemm") and gi < len(seq):
-            label, M, N, Kd = seq[gi]
+        if fam.startswith("gemm"):
+            label, M, N, Kd = seq[gi % len(seq)]
             gi += 1
             tf = 2.0 * M * N * Kd / (ms * 1e-3) / 1e12
             gb = 2.0 * (M * Kd + N * Kd + M * (N if "geglu" not in label else N // 2) + (M * N if "res" in label else 0)) / (ms * 1e-3) / 1e9
             note = f"{label:18s} M={M:6d} N={N:5d} K={Kd:5d}  {tf:7.1f} TFLOP/s ({tf / peak:5.1%})  min-traffic {gb:7.0f} GB/s"
         rows.append((fam, ms, note))
         print(f"{fam:14s} {ms * 1000:9.1f} us  {note}")
-    total = sum(ms for _, ms, _ in rows)
-    print(f"total {total:.3f} ms for batch {args.batch} -> {args.batch / total * 1000 / 99:.1f} img/s at 99 evaluations per image")
+    total = sum(ms for _, ms, _ in rows) / args.repeat
+    print(f"route: {'per-sample conditioning' if args.per_sample else 'shared conditioning row, fused RMSNorm'}; {args.repeat} evaluation(s) profiled")
+    print(f"total {total:.3f} ms per evaluation for batch {args.batch} -> {args.batch / total * 1000 / 99:.1f} img/s at 99 evaluations per image")
     by = {}
     for fam, ms, _ in rows:
-        by[fam] = by.get(fam, 0) + ms
+        by[fam] = by.get(fam, 0) + ms / args.repeat
     for fam, ms in sorted(by.items(), key=lambda kv: -kv[1]):
         print(f"  {fam:14s} {ms:8.3f} ms  {ms / total:6.1%}")
     if args.json:
