@@ -81,6 +81,10 @@ int kdb_solver_dpmpp_2m_step(const float* x, const float* den, const float* old_
 int kdb_solver_lincomb(const float* const* in_host, const float* coef_host, int n_in, float* out,
                        int64_t n, void* stream);
 
+/* out = uncond + (cond - uncond) * scale: classifier-free guidance combine of the two halves of a doubled batch
+ * (train.py:333-344 make_cfg_model_fn), same operation order as the reference. */
+int kdb_solver_cfg_combine(const float* uncond, const float* cond, float* out, int64_t n, float scale, void* stream);
+
 /* out[b,...] = (x[b,...] - den[b,...]) / sigma[b]      (sampling.py:46-48 to_d; sigma is [B]) */
 int kdb_solver_to_d(const float* x, const float* den, const float* sigma, float* out,
                     int batch, int64_t per_sample, void* stream);
@@ -199,9 +203,12 @@ int kdb_gemm_bf16_geglu(const void* a_bf16, const void* w_il_bf16, void* c_bf16,
 
 /* out[B,h,w,nh*e] = attention(qkv[B,h,w,3*nh*e]) on fp32 or bf16 token tensors, feature order
  * (t nh e) as produced by qkv_proj (image_transformer_v2.py:377,386,422,431,467). q/k must already be
- * cosine-normalised and rotated.  attn_type/attn_param/shift as in KdbModelConfig (:523 for shift). */
+ * cosine-normalised and rotated.  attn_type/attn_param/shift as in KdbModelConfig (:523 for shift).
+ * logit_bound (tensor-core path only, may be NULL): [n_heads] device floats, each in (0, 40], with |q . k| <= bound for that
+ * head -- for cosine-similarity attention the layer's `scale` parameter (:106-114).  The kernels then use the bound as
+ * softmax's fixed shift (one pass over the keys, no row maximum); NULL keeps the exact two-pass row-maximum kernels. */
 int kdb_attention(int precision, int fast, const void* qkv, void* out, int batch, int h, int w, int n_heads, int d_head,
-                  int attn_type, int attn_param, int shift, void* stream);
+                  int attn_type, int attn_param, int shift, const float* logit_bound, void* stream);
 
 #ifdef __cplusplus
 }

@@ -30,6 +30,7 @@ struct LayerPlan {
   bf16 *qkv_wb = nullptr, *out_wb = nullptr, *up_wb = nullptr, *down_wb = nullptr;
   bf16* up_wb_il = nullptr;          // up_proj rows interleaved (value/gate) for the fused GEGLU epilogue
   int exec_index = 0;                // position in execution order (indexes PosTables::rope)
+  bool bounded = false;              // every scale[h] in (0, KDB_ATTN_MAX_BOUND]: the scale is the attention kernels' fixed softmax shift
   bf16 *qkv_wf = nullptr, *up_wf = nullptr;   // per-evaluation copies with the AdaRMSNorm channel scale folded in (fused norm)
 };
 
@@ -154,6 +155,13 @@ int plan_layer(KdbModel* m, LayerPlan& L, const std::string& prefix, int level, 
     GET(a + "out_proj.weight", &L.out_w, L.C, L.C);
     L.ada_attn = *ada_off;
     *ada_off += L.C;
+    {   // |q . k| <= scale_h after the cosine-similarity normalisation: usable as a fixed softmax shift while exp(-2 scale) stays normal
+      std::vector<float> hs((size_t)L.nh);
+      KDB_CUDA(cudaMemcpyAsync(hs.data(), L.scale, sizeof(float) * L.nh, cudaMemcpyDeviceToHost, st));
+      KDB_CUDA(cudaStreamSynchronize(st));
+      L.bounded = true;
+      for (float v : hs) L.bounded = L.bounded && v > 0.f && v <= KDB_ATTN_MAX_BOUND;
+    }
     int rc;
     if ((rc = make_bf16(m, L.qkv_w, 3LL * L.C * L.C, &L.qkv_wb, st))) return rc;
     if ((rc = make_bf16(m, L.out_w, (int64_t)L.C * L.C, &L.out_wb, st))) return rc;
@@ -378,7 +386,8 @@ int run_layer(KdbModel* m, const LayerPlan& L, T* x, int B, int h, int w, const 
       }
     }
     if ((rc = tap<T>(m, tag + ".qkv", qkv, M * 3 * C, st))) return rc;
-    if ((rc = attention_dispatch<T>(qkv, ao, B, h, w, L.nh, L.e, L.attn_type, L.attn_param, L.shift, st))) return rc;
+    // the bound holds for q, k normalised by the fused QKV epilogue or by qknorm_rope (both paths above)
+    if ((rc = attention_dispatch<T>(qkv, ao, B, h, w, L.nh, L.e, L.attn_type, L.attn_param, L.shift, st, L.bounded ? L.scale : nullptr))) return rc;
     if ((rc = tap<T>(m, tag + ".ao", ao, M * C, st))) return rc;
     GemmEpi e;
     e.mode = EPI_RESID;
@@ -761,7 +770,7 @@ int kdb_model_debug_tap(KdbModel* m, const char* name, float* out, int64_t capac
 int64_t kdb_model_tap_count(const KdbModel* m) { return m ? m->tap_count : 0; }
 
 int kdb_attention(int precision, int fast, const void* qkv, void* out, int batch, int h, int w, int n_heads, int d_head, int attn_type,
-                  int attn_param, int shift, void* stream) {
+                  int attn_param, int shift, const float* logit_bound, void* stream) {
   KDB_REQUIRE(qkv && out && batch > 0 && h > 0 && w > 0 && n_heads > 0 && d_head > 0, KDB_ERR_BAD_ARG, "attention: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   if (precision == KDB_PREC_FP32) {
@@ -773,7 +782,7 @@ int kdb_attention(int precision, int fast, const void* qkv, void* out, int batch
     KDB_REQUIRE(tc_attention_supported(h, w, n_heads, d_head, attn_type, attn_param), KDB_ERR_UNSUPPORTED,
                 "attention: shape not covered by the tensor-core kernels");
     return launch_attention_tc(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), batch, h, w, n_heads, d_head, attn_type,
-                               attn_param, shift, st);
+                               attn_param, shift, st, logit_bound);
   }
   return launch_attention_generic<bf16>(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), batch, h, w, n_heads, d_head, attn_type,
                                         attn_param, shift, st);

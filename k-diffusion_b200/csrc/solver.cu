@@ -55,7 +55,7 @@ void count_launch(int family, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 // elementwise engine
 // ------------------------------------------------------------------------------------------------
-enum EwOp { OP_EULER = 0, OP_EULER_NOISE, OP_HEUN2, OP_DPMPP2M, OP_DPMPP2M_1, OP_LINCOMB };
+enum EwOp { OP_EULER = 0, OP_EULER_NOISE, OP_HEUN2, OP_DPMPP2M, OP_DPMPP2M_1, OP_LINCOMB, OP_CFG };
 
 struct EwParams {
   const float* in[6];
@@ -77,6 +77,8 @@ __device__ __forceinline__ float ew_apply(const EwParams& p, const float (&v)[6]
     return p.c[0] * v[0] - p.c[1] * (p.c[2] * v[1] + p.c[3] * v[2]);
   } else if constexpr (OP == OP_DPMPP2M_1) {      // a x - b den
     return p.c[0] * v[0] - p.c[1] * v[1];
+  } else if constexpr (OP == OP_CFG) {            // uncond + (cond - uncond) * scale  (reference train.py:341)
+    return v[0] + (v[1] - v[0]) * p.c[0];
   } else {
     float acc = p.c[0] * v[0];
 #pragma unroll
@@ -92,6 +94,7 @@ template <> struct EwArity<OP_EULER_NOISE> { static constexpr int value = 3; };
 template <> struct EwArity<OP_HEUN2> { static constexpr int value = 4; };
 template <> struct EwArity<OP_DPMPP2M> { static constexpr int value = 3; };
 template <> struct EwArity<OP_DPMPP2M_1> { static constexpr int value = 2; };
+template <> struct EwArity<OP_CFG> { static constexpr int value = 2; };
 
 constexpr int kEwThreads = 256;
 constexpr int kEwUnroll = 4;
@@ -375,6 +378,12 @@ int kdb_solver_euler_step(const float* x, const float* den, const float* noise, 
   p.in[0] = x; p.in[1] = den; p.in[2] = noise; p.out = x_out; p.c[0] = r; p.c[1] = cn; p.n = n;
   if (noise) return ew_launch<OP_EULER_NOISE>(p, 3, (cudaStream_t)stream);
   return ew_launch<OP_EULER>(p, 2, (cudaStream_t)stream);
+}
+
+int kdb_solver_cfg_combine(const float* uncond, const float* cond, float* out, int64_t n, float scale, void* stream) {
+  EwParams p{};
+  p.in[0] = uncond; p.in[1] = cond; p.out = out; p.c[0] = scale; p.n = n;
+  return ew_launch<OP_CFG>(p, 2, (cudaStream_t)stream);
 }
 
 int kdb_solver_heun_correct(const float* x, const float* den1, const float* x2, const float* den2, float* x_out, int64_t n,

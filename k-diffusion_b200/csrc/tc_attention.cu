@@ -36,6 +36,10 @@ constexpr int NA_BLK_KEYS = NA_BLK_ROWS * NA_KW;
 
 struct AttnParams {
   bf16* out;
+  // [nh] or nullptr: upper bound of |q . k| per head.  q and k are cosine-normalised (|q| = |k| = sqrt(scale_h), reference
+  // :106-114, RoPE is a rotation), so the layer's scale IS that bound and softmax can use it as a FIXED shift: exp(s - bound)
+  // needs no row maximum -> GLOBAL / NA run ONE pass over the key blocks instead of two, WINDOW skips its max scan.
+  const float* bound;
   int B, h, w, nh, shift, nblk;
 };
 
@@ -48,7 +52,7 @@ __device__ __forceinline__ uint32_t p_offset(int row, int chunk16) {   // byte o
   return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk16 ^ (row & 7)) << 4));
 }
 
-template <int MODE>
+template <int MODE, bool BOUNDED>
 __global__ void __launch_bounds__(160, MODE == MODE_WINDOW ? 4 : 2) attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_kv,
                                                                                       const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -83,7 +87,8 @@ __global__ void __launch_bounds__(160, MODE == MODE_WINDOW ? 4 : 2) attn_tc_kern
     c0 = min(max(qj0 - 3, 0), p.w - NA_KW);
   }
   const int nblk = (MODE == MODE_WINDOW) ? 1 : p.nblk;
-  const bool two_pass = nblk > 1;
+  constexpr bool bounded = BOUNDED;
+  const bool two_pass = nblk > 1 && !bounded;
 
   if (threadIdx.x == 0) {
     tc::tma_prefetch_desc(&tmap);
@@ -226,12 +231,13 @@ __global__ void __launch_bounds__(160, MODE == MODE_WINDOW ? 4 : 2) attn_tc_kern
           tc::tc_fence_before();
           tc::mbar_arrive(&bars->sc);
         } else if constexpr (MODE != MODE_WINDOW) {
+          if constexpr (bounded) m = __ldg(p.bound + head0);
           const float mb = m * LOG2E;
 #pragma unroll 1
           for (int c = 0; c < 4; ++c) {
             float v[32];
             tc::tmem_ld32(tmem_s + lane_base + c * 32, v);
-            if (!two_pass && c == 0) {   // single block: the row maximum comes from this very tile (two more reads are cheap)
+            if (!two_pass && !bounded && c == 0) {   // single block: the row maximum comes from this very tile (two more reads are cheap)
               float mm = -INFINITY;
 #pragma unroll 1
               for (int c2 = 0; c2 < 4; ++c2) {
@@ -242,7 +248,7 @@ __global__ void __launch_bounds__(160, MODE == MODE_WINDOW ? 4 : 2) attn_tc_kern
               }
               m = mm;
             }
-            const float mbb = two_pass ? mb : m * LOG2E;
+            const float mbb = (two_pass || bounded) ? mb : m * LOG2E;
             uint32_t pk[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -271,12 +277,16 @@ __global__ void __launch_bounds__(160, MODE == MODE_WINDOW ? 4 : 2) attn_tc_kern
 #pragma unroll
             for (int i = 0; i < 32; ++i) { v[i] = t0[i]; v[32 + i] = t1[i]; }
           }
+          if constexpr (!bounded) {
 #pragma unroll
-          for (int i = 0; i < 64; ++i) {
-            const int kq = i >> 4;
-            const bool ok = (!seam_r || ((kq >> 1) == (quad >> 1))) && (!seam_c || ((kq & 1) == (quad & 1)));
-            v[i] = ok ? v[i] : -INFINITY;
-            m = fmaxf(m, v[i]);
+            for (int i = 0; i < 64; ++i) {
+              const int kq = i >> 4;
+              const bool ok = (!seam_r || ((kq >> 1) == (quad >> 1))) && (!seam_c || ((kq & 1) == (quad & 1)));
+              v[i] = ok ? v[i] : -INFINITY;
+              m = fmaxf(m, v[i]);
+            }
+          } else {
+            m = __ldg(p.bound + head0 + hd);          // fixed shift: no maximum scan; masked keys get p = 0 below
           }
           const float mb = m * LOG2E;
           uint8_t* own = sP + hd * TILE_BYTES;
@@ -284,9 +294,18 @@ __global__ void __launch_bounds__(160, MODE == MODE_WINDOW ? 4 : 2) attn_tc_kern
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
             uint32_t pk[4];
+            bool ok = true;                        // (bounded) seam mask of this 8-key group: zero probability instead of -inf logit
+            if constexpr (bounded) {
+              const int kq = jj >> 1;
+              ok = (!seam_r || ((kq >> 1) == (quad >> 1))) && (!seam_c || ((kq & 1) == (quad & 1)));
+            }
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-              const float p0 = exp2f(fmaf(v[jj * 8 + 2 * t], LOG2E, -mb)), p1 = exp2f(fmaf(v[jj * 8 + 2 * t + 1], LOG2E, -mb));
+              float p0 = exp2f(fmaf(v[jj * 8 + 2 * t], LOG2E, -mb)), p1 = exp2f(fmaf(v[jj * 8 + 2 * t + 1], LOG2E, -mb));
+              if constexpr (bounded) {
+                p0 = ok ? p0 : 0.f;
+                p1 = ok ? p1 : 0.f;
+              }
               pk[t] = tc::pack_bf16x2(p0, p1);
               float q0, q1;
               tc::unpack_bf16x2(pk[t], q0, q1);
@@ -345,7 +364,7 @@ __global__ void __launch_bounds__(160, MODE == MODE_WINDOW ? 4 : 2) attn_tc_kern
   }
 }
 
-#include "tc_attention_persist.cuh"
+#include "tc_attention_pipe.cuh"
 
 constexpr size_t ATTN_SMEM = 5 * TILE_BYTES + 1024 + 128;          // GLOBAL
 constexpr size_t ATTN_SMEM_WINDOW = 3 * TILE_BYTES + 1024 + 128;   // WINDOW (P aliases Q,K)
@@ -368,6 +387,13 @@ bool tc_attention_supported(int h, int w, int nh, int e, int attn_type, int attn
 
 // programmatic dependent launch: barrier init / TMEM allocation overlap the tail of the qkv projection (KDB200_NO_PDL=1 disables)
 template <int MODE>
+static cudaError_t set_attn_smem(size_t smem) {
+  cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(attn_tc_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+template <int MODE>
 static cudaError_t launch_attn(dim3 grid, size_t smem, cudaStream_t st, const CUtensorMap& tq, const CUtensorMap& tkv, const AttnParams& p) {
   static const bool no_pdl = [] {
     const char* e = getenv("KDB200_NO_PDL");
@@ -383,11 +409,12 @@ static cudaError_t launch_attn(dim3 grid, size_t smem, cudaStream_t st, const CU
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   lc.attrs = attr;
   lc.numAttrs = no_pdl ? 0 : 1;
-  return cudaLaunchKernelEx(&lc, attn_tc_kernel<MODE>, tq, tkv, p);
+  if (p.bound != nullptr) return cudaLaunchKernelEx(&lc, attn_tc_kernel<MODE, true>, tq, tkv, p);
+  return cudaLaunchKernelEx(&lc, attn_tc_kernel<MODE, false>, tq, tkv, p);
 }
 
 int launch_attention_tc(const bf16* qkv, bf16* out, int B, int h, int w, int nh, int e, int attn_type, int attn_param, int shift,
-                        cudaStream_t st) {
+                        cudaStream_t st, const float* logit_bound) {
   KDB_REQUIRE(tc_attention_supported(h, w, nh, e, attn_type, attn_param), KDB_ERR_UNSUPPORTED, "attention_tc: unsupported shape");
   KDB_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, KDB_ERR_BAD_ARG,
               "attention_tc: operands must be 16-byte aligned");
@@ -395,6 +422,17 @@ int launch_attention_tc(const bf16* qkv, bf16* out, int B, int h, int w, int nh,
   AttnParams p{};
   p.out = out;
   p.B = B; p.h = h; p.w = w; p.nh = nh; p.shift = shift;
+  p.bound = logit_bound;
+  // persistent pipelined kernels (tc_attention_pipe.cuh) need the logit bound; KDB200_ATTN_ONESHOT=1 keeps the one-shot kernels (A/B)
+  static const bool oneshot = [] {
+    const char* e_ = getenv("KDB200_ATTN_ONESHOT");
+    return e_ != nullptr && e_[0] == '1';
+  }();
+  const bool use_pipe = logit_bound != nullptr && !oneshot;
+  PipeAttnParams pp{};
+  pp.out = out;
+  pp.bound = logit_bound;
+  pp.B = B; pp.h = h; pp.w = w; pp.nh = nh; pp.shift = shift;
   CUtensorMap tm;
   static bool attr_w = false, attr_g = false;
   if (attn_type == KDB_ATTN_SHIFTED_WINDOW) {
@@ -405,33 +443,15 @@ int launch_attention_tc(const bf16* qkv, bf16* out, int B, int h, int w, int nh,
     int rc = make_tmap_bf16(&tm, qkv, 4, dims, strides, shift == 0 ? box_f : box_q);
     if (rc) return rc;
     if (!attr_w) {
-      KDB_CUDA(cudaFuncSetAttribute(attn_tc_kernel<MODE_WINDOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATTN_SMEM_WINDOW));
+      KDB_CUDA(set_attn_smem<MODE_WINDOW>(ATTN_SMEM_WINDOW));
       attr_w = true;
     }
     p.nblk = 1;
-    const char* pe = getenv("KDB200_ATTN_PERSIST");      // experimental persistent variant (default off), read per call so tests can A/B
-    if (pe != nullptr && pe[0] == '1') {
-      static bool attr_p = false;
-      if (!attr_p) {
-        KDB_CUDA(cudaFuncSetAttribute(attn_window_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATTN_SMEM_WINDOW_PERSIST));
-        attr_p = true;
-      }
-      const int n_units = B * (h / 8) * (w / 8) * (nh / 2);
-      int sms = 0, dev = 0;
-      KDB_CUDA(cudaGetDevice(&dev));
-      KDB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-      const int grid_p = n_units < 2 * sms ? n_units : 2 * sms;
-      cudaLaunchConfig_t lc{};
-      lc.gridDim = dim3((unsigned)grid_p);
-      lc.blockDim = dim3(160);
-      lc.dynamicSmemBytes = ATTN_SMEM_WINDOW_PERSIST;
-      lc.stream = st;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      attr[0].val.programmaticStreamSerializationAllowed = 1;
-      lc.attrs = attr;
-      lc.numAttrs = 1;
-      KDB_CUDA(cudaLaunchKernelEx(&lc, attn_window_persist_kernel, tm, p, n_units));
+    if (use_pipe && (((int64_t)B * (h / 8) * (w / 8) * (nh / 2)) & 1) == 0) {
+      pp.nb = 1;
+      pp.n_pairs = (int)(((int64_t)B * (h / 8) * (w / 8) * (nh / 2)) / 2);
+      int prc = launch_attn_pipe<MODE_WINDOW>(tm, tm, pp, st);
+      if (prc) return prc;
       KDB_LAUNCH_CHECK(F_ATTN_TC, st);
       return 0;
     }
@@ -447,8 +467,16 @@ int launch_attention_tc(const bf16* qkv, bf16* out, int B, int h, int w, int nh,
     if (rc) return rc;
     if ((rc = make_tmap_bf16(&tkv, qkv, 4, dims, strides, box_kv))) return rc;
     if (!attr_n) {
-      KDB_CUDA(cudaFuncSetAttribute(attn_tc_kernel<MODE_NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATTN_SMEM));
+      KDB_CUDA(set_attn_smem<MODE_NA>(ATTN_SMEM));
       attr_n = true;
+    }
+    if (use_pipe && (((int64_t)B * nh * (h / NA_QH) * (w / NA_QW)) & 1) == 0) {
+      pp.nb = 3;
+      pp.n_pairs = (int)(((int64_t)B * nh * (h / NA_QH) * (w / NA_QW)) / 2);
+      int prc = launch_attn_pipe<MODE_NA>(tm, tkv, pp, st);
+      if (prc) return prc;
+      KDB_LAUNCH_CHECK(F_ATTN_TC, st);
+      return 0;
     }
     p.nblk = 3;      // 14 halo rows = 5 + 5 + 4
     dim3 grid((unsigned)((h / NA_QH) * (w / NA_QW)), (unsigned)nh, (unsigned)B);
@@ -461,8 +489,16 @@ int launch_attention_tc(const bf16* qkv, bf16* out, int B, int h, int w, int nh,
     int rc = make_tmap_bf16(&tm, qkv, 3, dims, strides, box);
     if (rc) return rc;
     if (!attr_g) {
-      KDB_CUDA(cudaFuncSetAttribute(attn_tc_kernel<MODE_GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATTN_SMEM));
+      KDB_CUDA(set_attn_smem<MODE_GLOBAL>(ATTN_SMEM));
       attr_g = true;
+    }
+    if (use_pipe && T % 256 == 0) {
+      pp.nb = (int)(T / ROWS);
+      pp.n_pairs = B * nh * (int)(T / 256);
+      int prc = launch_attn_pipe<MODE_GLOBAL>(tm, tm, pp, st);
+      if (prc) return prc;
+      KDB_LAUNCH_CHECK(F_ATTN_TC, st);
+      return 0;
     }
     p.nblk = (int)(T / ROWS);
     dim3 grid((unsigned)(T / ROWS), (unsigned)nh, (unsigned)B);

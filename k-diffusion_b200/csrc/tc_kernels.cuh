@@ -37,19 +37,23 @@ int launch_patch_in_tc(const float* x, const float* sigma, float sigma_data, con
                        float* ss_out, cudaStream_t st);
 
 bool tc_attention_supported(int h, int w, int nh, int e, int attn_type, int attn_param);
+// logit_bound: [nh] device floats with |q . k| <= bound per head (the layer's cosine-similarity scale), or nullptr.  With a bound the
+// kernels use it as softmax's fixed shift (single pass, no row maximum); the caller guarantees bound <= KDB_ATTN_MAX_BOUND.
+constexpr float KDB_ATTN_MAX_BOUND = 40.f;
 int launch_attention_tc(const bf16* qkv, bf16* out, int B, int h, int w, int nh, int e, int attn_type, int attn_param, int shift,
-                        cudaStream_t st);
+                        cudaStream_t st, const float* logit_bound = nullptr);
 
 template <typename T>
 inline int attention_dispatch(const T* qkv, T* out, int B, int h, int w, int nh, int e, int attn_type, int attn_param, int shift,
-                              cudaStream_t st) {
+                              cudaStream_t st, const float* logit_bound = nullptr) {
+  (void)logit_bound;
   return launch_attention_generic<T>(qkv, out, B, h, w, nh, e, attn_type, attn_param, shift, st);
 }
 template <>
 inline int attention_dispatch<bf16>(const bf16* qkv, bf16* out, int B, int h, int w, int nh, int e, int attn_type, int attn_param,
-                                    int shift, cudaStream_t st) {
+                                    int shift, cudaStream_t st, const float* logit_bound) {
   if (tc_attention_supported(h, w, nh, e, attn_type, attn_param))
-    return launch_attention_tc(qkv, out, B, h, w, nh, e, attn_type, attn_param, shift, st);
+    return launch_attention_tc(qkv, out, B, h, w, nh, e, attn_type, attn_param, shift, st, logit_bound);
   return launch_attention_generic<bf16>(qkv, out, B, h, w, nh, e, attn_type, attn_param, shift, st);
 }
 

@@ -45,6 +45,7 @@ SIGNATURES = {
     "kdb_solver_heun_correct": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _vp]),
     "kdb_solver_dpmpp_2m_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _vp]),
     "kdb_solver_lincomb": (_i32, [ctypes.POINTER(_vp), ctypes.POINTER(_f32), _i32, _vp, _i64, _vp]),
+    "kdb_solver_cfg_combine": (_i32, [_vp, _vp, _vp, _i64, _f32, _vp]),
     "kdb_solver_to_d": (_i32, [_vp, _vp, _vp, _vp, _i32, _i64, _vp]),
     "kdb_precond_scale_in": (_i32, [_vp, _vp, _f32, _vp, _i32, _i64, _vp]),
     "kdb_precond_combine": (_i32, [_vp, _vp, _vp, _f32, _vp, _i32, _i64, _vp]),
@@ -62,7 +63,7 @@ SIGNATURES = {
     "kdb_model_tap_count": (_i64, [_vp]),
     "kdb_gemm_bf16": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "kdb_gemm_bf16_geglu": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
-    "kdb_attention": (_i32, [_i32, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "kdb_attention": (_i32, [_i32, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
 }
 
 _lib = None
@@ -229,6 +230,15 @@ def lincomb(tensors, coefs, out=None):
     ptrs = (_vp * n)(*[t.data_ptr() for t in tensors])
     cs = (_f32 * n)(*[float(c) for c in coefs])
     check(lib().kdb_solver_lincomb(ptrs, cs, n, ptr(out), tensors[0].numel(), stream()))
+    return out
+
+
+@_on_device_of_first
+def cfg_combine(uncond, cond, scale, out=None):
+    """uncond + (cond - uncond) * scale"""
+    require_cuda(uncond, cond)
+    out = _out_like(uncond, out)
+    check(lib().kdb_solver_cfg_combine(ptr(uncond), ptr(cond), ptr(out), uncond.numel(), float(scale), stream()))
     return out
 
 
@@ -429,12 +439,14 @@ def gemm_bf16_geglu(a, w_up, ss_in=None):
 
 
 @_on_device_of_first
-def attention(qkv, h, w, n_heads, d_head, attn_type, attn_param=0, shift=0, fast=False):
-    """qkv [B, h*w, 3*n_heads*d_head] (fp32 or bf16, q/k already normalised + rotated) -> [B, h*w, n_heads*d_head]."""
-    require_cuda(qkv)
+def attention(qkv, h, w, n_heads, d_head, attn_type, attn_param=0, shift=0, fast=False, logit_bound=None):
+    """qkv [B, h*w, 3*n_heads*d_head] (fp32 or bf16, q/k already normalised + rotated) -> [B, h*w, n_heads*d_head].
+    logit_bound: optional fp32 [n_heads] with |q . k| <= bound (the cosine-similarity scale): single-pass fixed-shift softmax."""
+    require_cuda(qkv, logit_bound)
     prec = PREC_BF16 if qkv.dtype == torch.bfloat16 else PREC_FP32
     B = qkv.shape[0]
     out = torch.empty(B, h * w, n_heads * d_head, dtype=qkv.dtype, device=qkv.device)
     code = _ATTN_CODE[attn_type] if isinstance(attn_type, str) else attn_type
-    check(lib().kdb_attention(prec, 1 if fast else 0, ptr(qkv.contiguous()), ptr(out), B, h, w, n_heads, d_head, code, attn_param, shift, stream()))
+    check(lib().kdb_attention(prec, 1 if fast else 0, ptr(qkv.contiguous()), ptr(out), B, h, w, n_heads, d_head, code, attn_param, shift,
+                               ptr(logit_bound), stream()))
     return out

@@ -70,3 +70,43 @@ def gather_samples(x, group=None):
     out = [torch.empty_like(x) for _ in range(dist.get_world_size(group))]
     dist.all_gather(out, x.contiguous(), group=group)
     return torch.cat(out)
+
+
+class ProcessGroup:
+    """The slice of `accelerate.Accelerator` the sampling driver uses (reference sample.py:37-66, evaluation.py:80-90):
+    `device`, `num_processes`, `process_index`, `is_main_process`, `is_local_main_process`, `gather`, `print`,
+    `wait_for_everyone`.  One process per GPU; initialises torch.distributed (NCCL) from the torchrun environment when
+    WORLD_SIZE > 1, otherwise it is a single-process stand-in."""
+
+    def __init__(self, backend=None):
+        import os
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_process_index = int(os.environ.get("LOCAL_RANK", "0"))
+        self.device = torch.device("cuda", self.local_process_index) if torch.cuda.is_available() else torch.device("cpu")
+        if self.device.type == "cuda":
+            torch.cuda.set_device(self.device)
+        if world > 1 and not dist.is_initialized():
+            backend = backend or ("nccl" if self.device.type == "cuda" else "gloo")
+            kw = dict(device_id=self.device) if backend == "nccl" else {}
+            dist.init_process_group(backend, **kw)
+        self.num_processes = dist.get_world_size() if dist.is_initialized() else 1
+        self.process_index = dist.get_rank() if dist.is_initialized() else 0
+
+    @property
+    def is_main_process(self):
+        return self.process_index == 0
+
+    @property
+    def is_local_main_process(self):
+        return self.local_process_index == 0
+
+    def gather(self, x):
+        return gather_samples(x)
+
+    def print(self, *args, **kwargs):
+        if self.is_main_process:
+            print(*args, **kwargs)
+
+    def wait_for_everyone(self):
+        if dist.is_initialized():
+            dist.barrier()

@@ -428,6 +428,38 @@ def plan_dpmpp_3m_sde(sig, eta=1., s_noise=1.):
 
 
 # --------------------------------------------------------------------------------------------
+# classifier-free guidance (reference train.py:333-344 make_cfg_model_fn)
+# --------------------------------------------------------------------------------------------
+
+class CFGDenoiser:
+    """model_fn(x, sigma, class_cond) = uncond + (cond - uncond) * cfg_scale on a doubled batch [uncond | cond].
+
+    `num_classes` is the index of the unconditional token (class_emb has num_classes + 1 rows, reference config.py:208).
+    Called directly it works around ANY `model(x, sigma, class_cond=...)`.  Passed to a sampler of this package with a native
+    `Denoiser` inside, the sampler evaluates the doubled batch in one engine call per step (conditioning rows of all steps
+    precomputed) and the whole loop, guidance included, is captured into one CUDA graph."""
+
+    def __init__(self, model, cfg_scale, num_classes):
+        self.inner_model, self.cfg_scale, self.num_classes = model, float(cfg_scale), int(num_classes)
+
+    def double(self, x, sigma, class_cond):
+        return torch.cat([x, x]), torch.cat([sigma, sigma]), torch.cat([torch.full_like(class_cond, self.num_classes), class_cond])
+
+    def __call__(self, x, sigma, class_cond):
+        x_in, sigma_in, cc = self.double(x, sigma, class_cond)
+        out = self.inner_model(x_in, sigma_in, class_cond=cc)
+        out_uncond, out_cond = out.chunk(2)
+        if not out.is_cuda:
+            raise RuntimeError("k_diffusion (B200-native) operates on CUDA tensors only; there is no CPU fallback")
+        return _native.cfg_combine(_native.f32c(out_uncond), _native.f32c(out_cond), self.cfg_scale)
+
+
+def make_cfg_model_fn(model, cfg_scale, num_classes):
+    """Same contract as the closure in reference train.py:333-344: returns `model` itself when cfg_scale == 1."""
+    return CFGDenoiser(model, cfg_scale, num_classes) if cfg_scale != 1 else model
+
+
+# --------------------------------------------------------------------------------------------
 # loop runner
 # --------------------------------------------------------------------------------------------
 
@@ -435,18 +467,24 @@ _NATIVE_KW = {"aug_cond", "class_cond", "mapping_cond"}
 _GRAPH_ENV = "KDB200_CUDA_GRAPH"
 
 
+_COND_TABLE_BYTES = 1 << 30         # precompute the per-sample conditioning rows of ALL evaluations up to this size
+
+
 class _Evaluator:
     """denoised = D(x, sigma_k) for the k-th model evaluation of a plan."""
 
     def __init__(self, model, x, extra_args, eval_sigmas):
         from .layers import Denoiser
+        self.cfg = model if isinstance(model, CFGDenoiser) else None
+        base = model.inner_model if self.cfg is not None else model
         self.model, self.extra_args = model, extra_args
         self.B = x.shape[0]
-        self.native = isinstance(model, Denoiser) and model.is_native() and set(extra_args) <= _NATIVE_KW
+        keys_ok = set(extra_args) == {"class_cond"} if self.cfg is not None else set(extra_args) <= _NATIVE_KW
+        self.native = isinstance(base, Denoiser) and base.is_native() and keys_ok
         sig = torch.tensor(eval_sigmas, dtype=torch.float32, device=x.device)
         self.sigma_rows = sig[:, None].expand(len(eval_sigmas), self.B).contiguous()
         if self.native:
-            inner = model.inner_model
+            inner = base.inner_model
             if x.ndim != 4:
                 raise ValueError(f"expected x of shape [B, C, H, W], got {tuple(x.shape)}")
             if inner.training and any(s.dropout > 0 for s in inner.levels):       # same checks as the module's own forward
@@ -455,26 +493,63 @@ class _Evaluator:
             self.inner, self.eng = inner, inner.engine()
             if inner.class_emb is not None and not torch.cuda.is_current_stream_capturing():
                 self.eng.check_class_range(extra_args.get("class_cond"))          # once per sampler call, outside the loop
+                if self.cfg is not None and not 0 <= self.cfg.num_classes < int(self.eng.cfg.num_classes):
+                    raise IndexError(f"CFG unconditional class {self.cfg.num_classes} outside class_emb ({int(self.eng.cfg.num_classes)} rows)")
             self.precision = inner.resolved_precision()
-            self.sigma_data = float(model.sigma_data)
+            self.sigma_data = float(base.sigma_data)
             self.per_sample = any(extra_args.get(k) is not None for k in _NATIVE_KW)
             self._sig_rows, self.table = sig, None                               # conditioning table: built on first use
+            self.n_evals = len(eval_sigmas)
+            if self.cfg is not None:                                             # doubled batch: [uncond | cond]
+                self.sigma_rows2 = sig[:, None].expand(self.n_evals, 2 * self.B).contiguous()
+                self._x2 = None
 
     def capturable(self):
         return self.native
+
+    def graph_tag(self):
+        return ("cfg", self.cfg.cfg_scale, self.cfg.num_classes) if self.native and self.cfg is not None else ()
 
     def static_args(self):
         """The per-sample conditioning tensors a captured graph reads ((name, tensor) pairs, stable order)."""
         return [(k, self.extra_args[k]) for k in sorted(_NATIVE_KW) if self.native and self.extra_args.get(k) is not None]
 
+    def _cond_args(self, rows_per_eval, reps):
+        """aug / class / mapping conditioning tensors for `reps` evaluations (the doubled CFG batch included)."""
+        ea = self.extra_args
+        cc = ea.get("class_cond") if self.inner.class_emb is not None else None
+        if self.cfg is not None:
+            cc = torch.cat([torch.full_like(cc, self.cfg.num_classes), cc])
+        aug = ea.get("aug_cond")
+        mc = ea.get("mapping_cond") if self.inner.mapping_cond_in_proj is not None else None
+        rep_ = lambda t: None if t is None else (t if reps == 1 else t.repeat(reps, *([1] * (t.ndim - 1))))
+        return rep_(aug), rep_(cc), rep_(mc)
+
+    def _per_sample_rows(self, k, rows):
+        """Conditioning rows [rows, stride] of evaluation k.  All evaluations' rows come from ONE launch when they fit the
+        table budget (the conditioning kernel is a latency-bound chain of mat-vecs: ~1.5 ms whether it serves 64 rows or 6000)."""
+        stride = self.eng.cond_stride
+        sig_rows = self.sigma_rows2 if self.cfg is not None else self.sigma_rows
+        if self.n_evals * rows * stride * 4 <= _COND_TABLE_BYTES:
+            if self.table is None:
+                aug, cc, mc = self._cond_args(rows, self.n_evals)
+                self.table = self.eng.conditioning(sig_rows.reshape(-1), aug, cc, mc)
+            return self.table[k * rows:(k + 1) * rows]
+        aug, cc, mc = self._cond_args(rows, 1)
+        return self.eng.conditioning(sig_rows[k], aug, cc, mc)
+
     def __call__(self, k, x, out=None):
         if not self.native:
             return self.model(x, self.sigma_rows[k], **self.extra_args)
+        if self.cfg is not None:
+            if self._x2 is None or self._x2.shape[0] != 2 * self.B:
+                self._x2 = torch.empty(2 * self.B, *x.shape[1:], device=x.device, dtype=torch.float32)
+            torch.cat([x, x], out=self._x2)
+            cond = self._per_sample_rows(k, 2 * self.B)
+            both = self.eng.forward(self._x2, self.sigma_rows2[k], cond, self.eng.cond_stride, self.sigma_data, self.precision)
+            return _native.cfg_combine(both[:self.B], both[self.B:], self.cfg.cfg_scale, out=out)
         if self.per_sample:
-            cond = self.eng.conditioning(self.sigma_rows[k], self.extra_args.get("aug_cond"),
-                                         self.extra_args.get("class_cond") if self.inner.class_emb is not None else None,
-                                         self.extra_args.get("mapping_cond") if self.inner.mapping_cond_in_proj is not None else None)
-            stride = self.eng.cond_stride
+            cond, stride = self._per_sample_rows(k, self.B), self.eng.cond_stride
         else:
             if self.table is None:          # one launch for every evaluation of the schedule (a cached graph never needs it)
                 self.table = self.eng.conditioning(self._sig_rows)
@@ -529,7 +604,7 @@ def _noise_kind(noise_sampler):
 
 def _graph_key(name, ev, x, sig, params, noise_sampler):
     key = (name, id(ev.inner), ev.eng._sig, ev.sigma_data, tuple(x.shape), x.device.index, tuple(sig), ev.precision, params,
-           tuple((k, tuple(t.shape), str(t.dtype)) for k, t in ev.static_args()))
+           tuple((k, tuple(t.shape), str(t.dtype)) for k, t in ev.static_args()), ev.graph_tag())
     if _noise_kind(noise_sampler) == 'brownian':
         tr = noise_sampler.tree          # the entry keeps `transform` alive, so its id cannot be recycled while the key exists
         key += (('brownian', tr.t0, tr.t1, tr.sign, tr.depth, tr.batched, int(tr.seeds.numel()), id(noise_sampler.transform)),)
@@ -568,6 +643,8 @@ def _run(name, body, ev, x, sig, params, callback, noise_sampler=None):
             with torch.cuda.stream(side):                  # warm-up outside capture (allocations, pos tables)
                 body(entry.static_in)
             torch.cuda.current_stream().wait_stream(side)
+            if ev.static_args():
+                ev.table = None      # per-sample conditioning rows depend on the (refreshable) labels: their launch belongs INSIDE the graph
             entry.graph = torch.cuda.CUDAGraph()
             n0 = _native.launch_count()
             with torch.cuda.graph(entry.graph):

@@ -29,7 +29,18 @@ def _worker(rank, world, port, q):
     seeds = K.parallel.sample_seeds(5, lo, hi)
     shard = torch.tensor(seeds[:5], dtype=torch.int64)              # equal shard sizes: 5 + 5
     allv = K.parallel.gather_samples(shard)
-    q.put((rank, same, nbytes, allv.tolist()))
+    # the sampling driver (reference evaluation.py:80-90) over a 2-process group: every process "samples" a tensor
+    # that encodes (process, call, row); the gathered result must be [p0 batch0, p1 batch0, p0 batch1, ...] cut to n
+    pg = K.parallel.ProcessGroup.__new__(K.parallel.ProcessGroup)
+    pg.num_processes, pg.process_index, pg.local_process_index, pg.device = world, rank, rank, torch.device("cpu")
+    calls = [0]
+
+    def sample_fn(cur):
+        calls[0] += 1
+        return (1000 * rank + 100 * calls[0] + torch.arange(cur + 2)).float()[:, None]       # longer than asked: the driver trims
+
+    feats = K.evaluation.compute_features(pg, sample_fn, lambda t: t * 2, 11, 4)
+    q.put((rank, same, nbytes, allv.tolist(), feats.flatten().tolist()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -48,7 +59,12 @@ def test_two_rank_broadcast_and_shards():
         assert p.exitcode == 0
     sys.path.insert(0, str(ROOT / "k-diffusion_b200"))
     import k_diffusion as K
-    for rank, same, nbytes, allv in res:
+    want = []           # n = 11, P = 2 -> 6 per process in batches of 4 and 2 (cur = min(n - i, 4) as in the reference)
+    for call, cur in ((1, 4), (2, 4)):
+        for r in range(2):
+            want += [2.0 * (1000 * r + 100 * call + k) for k in range(cur)]
+    for rank, same, nbytes, allv, feats in res:
+        assert feats == want[:11], (feats, want[:11])
         assert same, f"rank {rank} weights differ from rank 0 after broadcast"
         assert nbytes > 4_000_000
         assert allv == K.parallel.sample_seeds(5, 0, 10)            # gather reproduces the unsharded seed list

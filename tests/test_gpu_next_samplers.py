@@ -143,3 +143,44 @@ def test_class_conditional_graph_equals_eager(monkeypatch):
     assert torch.equal(g1, e1) and torch.equal(g2, e2) and not torch.equal(g1, g2)
     with pytest.raises(IndexError, match="class_cond"):
         S.sample_heun(model, x, sigmas, extra_args=dict(class_cond=torch.tensor([0, 1, 2, 11], device=DEV)), disable=True)
+
+
+# ------------------------------------------------------------------------------------------
+# classifier-free guidance wrapper (reference train.py:333-344)
+# ------------------------------------------------------------------------------------------
+
+def test_cfg_wrapper_vs_oracle(monkeypatch):
+    """cfg1 (MNIST transformer, 10 classes + unconditional token, fp32 exact path): make_cfg_model_fn on the native model through
+    sample_dpmpp_2m_sde(eta=0, solver_type='heun') -- the sampler / settings of the reference's demo() -- against the oracle's
+    restatement of the closure, rtol 1e-3 / atol 1e-5; graph == eager; the wrapper called directly; cfg_scale == 1 returns the model."""
+    cfg, sd, inner, model, z = build("cfg1_mnist")
+    x, sigmas = z["x"].to(DEV), z["sigmas"].to(DEV)
+    cc = torch.tensor([0, 3, 7, 9])
+    oracle_model = O.make_denoiser(sd, cfg["model"])
+    o_fn = O.make_cfg_model_fn(oracle_model, 3.0, 10)
+    want = O.sample_dpmpp_2m_sde(o_fn, z["x"], z["sigmas"], noise_sampler=None, extra_args=dict(class_cond=cc), eta=0.0, solver_type="heun")
+    fn = S.make_cfg_model_fn(model, 3.0, 10)
+    assert S.make_cfg_model_fn(model, 1.0, 10) is model
+    S.clear_graph_cache()
+    got = S.sample_dpmpp_2m_sde(fn, x, sigmas, extra_args=dict(class_cond=cc.to(DEV)), eta=0.0, solver_type="heun", disable=True)
+    assert_close(got, want, what="cfg dpmpp_2m_sde (graph)")
+    ref = load_npz("cfg1_cfg.npz")            # recorded from the reference's own closure (oracle/make_golden_cfg.py), same inputs
+    assert torch.equal(ref["class_cond"], cc)
+    assert_close(got, ref["dpmpp_2m_sde_heun_eta0"], what="cfg dpmpp_2m_sde vs the reference closure")
+    assert_close(fn(x, ref["sigma"].to(DEV), class_cond=cc.to(DEV)), ref["model_fn"], what="cfg model_fn vs the reference closure")
+    # direct call == oracle closure on one evaluation
+    sig = torch.tensor([0.3, 1.0, 5.0, 40.0])
+    assert_close(fn(x, sig.to(DEV), class_cond=cc.to(DEV)), o_fn(z["x"], sig, class_cond=cc), what="cfg model_fn")
+    # new labels through the cached graph, against eager launches
+    cc2 = torch.tensor([1, 1, 2, 8], device=DEV)
+    g2 = S.sample_dpmpp_2m_sde(fn, x, sigmas, extra_args=dict(class_cond=cc2), eta=0.0, solver_type="heun", disable=True)
+    monkeypatch.setenv("KDB200_CUDA_GRAPH", "0")
+    e1 = S.sample_dpmpp_2m_sde(fn, x, sigmas, extra_args=dict(class_cond=cc.to(DEV)), eta=0.0, solver_type="heun", disable=True)
+    e2 = S.sample_dpmpp_2m_sde(fn, x, sigmas, extra_args=dict(class_cond=cc2), eta=0.0, solver_type="heun", disable=True)
+    assert torch.equal(got, e1) and torch.equal(g2, e2) and not torch.equal(got, g2)
+    # opaque models work through the same wrapper
+    toy = lambda xx, ss, class_cond: xx / (1 + ss[:, None, None, None] ** 2) * (1 + 0.1 * class_cond[:, None, None, None].float())
+    tfn = S.make_cfg_model_fn(toy, 2.0, 10)
+    xin, uncond = x, torch.full_like(cc2, 10)
+    ref = toy(xin, sig.to(DEV), uncond) + (toy(xin, sig.to(DEV), cc2) - toy(xin, sig.to(DEV), uncond)) * 2.0
+    assert_close(tfn(xin, sig.to(DEV), class_cond=cc2), ref, rtol=1e-5, atol=1e-6, what="cfg around an opaque model")

@@ -76,6 +76,34 @@ def test_attention_tcgen05_vs_reference(B, h, w, nh, kind, param, shift):
         assert float(err.max()) < 3e-2 and float(err.mean()) < 3e-3, f"{name}: max {float(err.max()):.4f} mean {float(err.mean()):.5f}"
 
 
+@pytest.mark.parametrize("B,h,w,nh,kind,param,shift", [
+    (2, 16, 16, 2, "shifted-window", 8, 0), (3, 64, 64, 2, "shifted-window", 8, 4), (1, 8, 8, 4, "shifted-window", 8, 4),
+    (2, 16, 16, 8, "global", 0, 0), (3, 16, 16, 8, "global", 0, 0), (1, 8, 16, 2, "global", 0, 0), (2, 32, 32, 4, "global", 0, 0),
+    (1, 32, 32, 16, "global", 0, 0), (5, 16, 32, 3, "global", 0, 0), (32, 16, 16, 8, "global", 0, 0),
+    (2, 16, 32, 2, "neighborhood", 7, 0), (1, 64, 64, 2, "neighborhood", 7, 0), (2, 32, 32, 4, "neighborhood", 7, 0),
+    # several tile pairs per CTA (persistent loop, Q double buffer, K/V ring wrap-around), odd tile counts (one-shot fallback)
+    (32, 64, 64, 2, "shifted-window", 8, 4), (32, 64, 64, 2, "shifted-window", 8, 0), (20, 32, 32, 4, "shifted-window", 8, 4),
+    (8, 64, 64, 2, "neighborhood", 7, 0), (6, 32, 32, 4, "neighborhood", 7, 0), (3, 24, 48, 1, "neighborhood", 7, 0),
+    (1, 16, 112, 3, "neighborhood", 7, 0), (1, 8, 8, 2, "shifted-window", 8, 4)])
+def test_attention_tcgen05_bounded_softmax(B, h, w, nh, kind, param, shift):
+    """Fixed-shift softmax (logit_bound = the cosine-similarity scale): single-pass kernels, the persistent pipelined global
+    kernel for S % 256 == 0 (several units per CTA at B = 32), against the same oracle and tolerance as the row-maximum kernels."""
+    from k_diffusion import _native as N_
+    qkv = _qkv(B, h, w, nh, seed=h * w + nh + shift + 1)
+    want = _ref_attention(qkv[:4], h, w, nh, kind, param, shift)
+    bound = torch.full([nh], 10.0, device=DEV)
+    fast = N_.attention(qkv, h, w, nh, 64, kind, param, shift, fast=True, logit_bound=bound)
+    torch.cuda.synchronize()
+    err = (fast[:4].float().cpu() - want).abs()
+    assert float(err.max()) < 3e-2 and float(err.mean()) < 3e-3, f"max {float(err.max()):.4f} mean {float(err.mean()):.5f}"
+    if B > 4:          # images beyond the oracle's slice: compare with the row-maximum kernel
+        slow = N_.attention(qkv, h, w, nh, 64, kind, param, shift, fast=True)
+        assert float((fast.float() - slow.float()).abs().max()) < 2e-2
+    # a looser bound (scale 20 on the same data) must give the same softmax: shift invariance
+    loose = N_.attention(qkv, h, w, nh, 64, kind, param, shift, fast=True, logit_bound=bound * 2)
+    assert float((loose.float() - fast.float()).abs().max()) < 2e-2
+
+
 def test_attention_generic_fp32_exact():
     from k_diffusion import _native as N_
     for kind, param, shift, h, w in (("global", 0, 0, 7, 7), ("shifted-window", 4, 2, 8, 12), ("neighborhood", 7, 0, 9, 12), ("neighborhood", 3, 0, 5, 4)):

@@ -262,15 +262,16 @@ def test_shard_helpers():
     assert P.sample_seeds(7, 4, 9) == full[4:9] and P.sample_seeds(8, 0, 16) != full
 
 
-def test_experimental_attention_barrier_protocol_model():
-    """tools/attn_protocol_sim.py: randomised interleavings of the persistent window-attention kernel's mbarrier protocol
-    (try_wait.parity semantics) must never alias a phase, deadlock, or refill a live buffer."""
+def test_attention_pipeline_barrier_protocol_model():
+    """tools/attn_pipe_protocol_sim.py: randomised interleavings of attn_pipe_kernel's mbarrier protocol (producer, MMA issuer, two
+    softmax groups, asynchronous TMA / MMA completion, try_wait.parity semantics) must never alias a phase, deadlock, overwrite a
+    live buffer or hand a consumer the wrong tile -- for shared K/V (global) and per-tile K/V (window nb = 1, neighbourhood nb = 3)."""
     import importlib.util
     from conftest import ROOT
-    spec = importlib.util.spec_from_file_location("attn_protocol_sim", ROOT / "tools" / "attn_protocol_sim.py")
+    spec = importlib.util.spec_from_file_location("attn_pipe_protocol_sim", ROOT / "tools" / "attn_pipe_protocol_sim.py")
     sim = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(sim)
-    for n_local in (0, 1, 2, 3, 4, 7):
-        for seed in range(40):
-            assert sim.run(n_local, seed)
-
+    for shared, nb in ((True, 2), (True, 8), (False, 1), (False, 3)):
+        for n_local in (0, 1, 2, 3, 7):
+            for seed in range(25):
+                assert sim.run(n_local, nb, shared, seed)

@@ -192,3 +192,16 @@ def test_neighborhood_definition_properties():
     g = torch.Generator().manual_seed(0)
     q, k, v = (torch.randn(2, 7, 7, 2, 8, generator=g) for _ in range(3))
     assert_close(O.neighborhood_attention(q, k, v, 7), O.global_attention(q, k, v), what="na==global")
+
+
+def test_cfg_wrapper_against_reference_closure():
+    """O.make_cfg_model_fn against outputs of the reference's own closure (train.py:333-344, executed from the
+    reference source by oracle/make_golden_cfg.py) on the cfg1 model: one call and the demo() sampler recipe."""
+    cfg, shapes, z = load_fixture("cfg1_mnist")
+    c = load_npz("cfg1_cfg.npz")
+    model = O.make_denoiser(synth_sd(shapes, 1), cfg["model"])
+    fn = O.make_cfg_model_fn(model, float(c["cfg_scale"]), int(c["num_classes"]))
+    assert O.make_cfg_model_fn(model, 1.0, 10) is model
+    assert_close(fn(z["x"], c["sigma"], class_cond=c["class_cond"]), c["model_fn"], what="cfg model_fn")
+    got = O.sample_dpmpp_2m_sde(fn, z["x"], z["sigmas"], noise_sampler=None, extra_args=dict(class_cond=c["class_cond"]), eta=0.0, solver_type="heun")
+    assert_close(got, c["dpmpp_2m_sde_heun_eta0"], what="cfg dpmpp_2m_sde")
