@@ -223,6 +223,49 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------
+# per-kernel device times of the graph-replayed step (CUPTI activity records through torch.profiler)
+# ------------------------------------------------------------------------------------------------
+def kernel_family(name):
+    """Kernel name (as CUPTI reports it) -> the family names of kdb_launch_breakdown."""
+    name = name.replace("(int)", "").replace(" ", "")
+    if "gemm_tc_kernel<64,5>" in name:
+        return "patch_out"
+    for key, fam in (("gemm_tc", "gemm_tc"), ("gemm_simt", "gemm_simt"), ("attn_", "attn_tc"), ("patch_in", "patch_in"), ("patch_out", "patch_out"),
+                     ("fold_norm", "fused_norm"), ("ew_kernel", "solver"), ("precond", "precond"), ("noise_", "noise"),
+                     ("conditioning", "cond"), ("rmsnorm", "rmsnorm"), ("qknorm", "qknorm_rope"), ("geglu_kernel", "geglu")):
+        if key in name:
+            return fam
+    return "other (torch copies)"
+
+
+def graph_kernel_times(fn):
+    """[(family, kernel name, start_us, duration_ms)] of every kernel `fn()` executes, in start order, from CUPTI activity records.
+    Unlike CUDA events between eager launches this times the kernels INSIDE the replayed CUDA graph: no event, no host launch gap,
+    programmatic-launch overlap as in the timed step.  Returns None when the profiler is unavailable."""
+    try:
+        from torch.autograd import DeviceType
+        from torch.profiler import ProfilerActivity, profile
+        fn()
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            fn()
+            torch.cuda.synchronize()
+        out = []
+        for e in prof.events():
+            if e.device_type != DeviceType.CUDA:
+                continue
+            name = e.name
+            if name.startswith("Memcpy") or name.startswith("Memset") or name.startswith("cudaGraph"):
+                continue
+            out.append((kernel_family(name), name, float(e.time_range.start), float(e.time_range.elapsed_us()) / 1000.0))
+        out.sort(key=lambda r: r[2])
+        return out or None
+    except Exception as exc:          # measurement aid only
+        print(f"bench: torch.profiler unavailable ({exc!r}); falling back to CUDA events between eager launches", file=sys.stderr)
+        return None
+
+
+# ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
 def main():
@@ -321,16 +364,34 @@ def main():
 
     roofline = cpu_baseline = breakdown = parity = None
     if rank == 0 and not args.no_extras:
-        # --- per-kernel device times of one sampler pass with a short schedule (same batch, same kernels): eager launches behind
-        # a gate (kdb_profile_gate) so the host runs ahead and the kernels execute back to back as under graph replay
-        prof_steps = 5 if wl["sampler"] == "heun" else 9
-        os.environ["KDB200_CUDA_GRAPH"] = "0"
-        run_sampler(x, prof_steps)
-        torch.cuda.synchronize()
-        with _native.profile(gate_ms=40.0 if RES <= 256 else 120.0) as prof:
+        # --- per-kernel device times.  Preferred: CUPTI activity records of ONE replay of the very graph that was timed (no events,
+        # no host gaps, programmatic-launch overlap included).  Fallback: CUDA events after every eager launch of a shorter schedule
+        # behind a gate kernel (kdb_profile_gate), which adds ~8 us of event / serialisation overhead per launch.
+        class _P:
+            pass
+        prof = _P()
+        recs = graph_kernel_times(lambda: run_sampler(x))
+        if recs is not None:
+            prof.launches = [(fam, ms_) for fam, _, _, ms_ in recs]
+            prof_evals, prof_how = NFE, ("CUPTI activity records (torch.profiler) of one replay of the timed CUDA graph: kernel durations "
+                                         "inside the graph, no events between kernels, no host launch gaps")
+            span_ms = (recs[-1][2] + recs[-1][3] * 1000.0 - recs[0][2]) / 1000.0
+        else:
+            prof_steps = 5 if wl["sampler"] == "heun" else 9
+            os.environ["KDB200_CUDA_GRAPH"] = "0"
             run_sampler(x, prof_steps)
-        os.environ["KDB200_CUDA_GRAPH"] = "1"
-        prof_evals = nfe_of(wl["sampler"], prof_steps)
+            torch.cuda.synchronize()
+            with _native.profile(gate_ms=40.0 if RES <= 256 else 120.0) as prof:
+                run_sampler(x, prof_steps)
+            os.environ["KDB200_CUDA_GRAPH"] = "1"
+            prof_evals = nfe_of(wl["sampler"], prof_steps)
+            prof_how = (f"CUDA events after every launch of one eager {SAMPLER_NAME[wl['sampler']]} with {prof_steps} Karras steps behind a gate kernel "
+                        "(each interval carries ~8 us of event / serialisation overhead)")
+            span_ms = None
+        prof.by_family = {}
+        for f_, t_ in prof.launches:
+            c_, tot_ = prof.by_family.get(f_, (0, 0.0))
+            prof.by_family[f_] = (c_ + 1, tot_ + t_)
         total = sum(t for _, t in prof.by_family.values())
         breakdown = {f: {"launches": c, "ms": round(t, 3), "share": round(t / total, 4)} for f, (c, t) in
                      sorted(prof.by_family.items(), key=lambda kv: -kv[1][1])}
@@ -387,11 +448,10 @@ def main():
                     "share_of_step": round(g_ms / total, 4), "traffic": traffic, "traffic_note": traffic_note, "by_shape": shapes,
                     "by_level": by_level, "attention": attn,
                     "profile_ms_per_eval": round(total / prof_evals, 4), "timed_ms_per_eval": round(ms / args.steps / NFE, 4),
-                    "how": f"CUDA events after every launch (on the launching stream) of one eager {SAMPLER_NAME[wl['sampler']]} with {prof_steps} Karras steps "
-                           "at the bench batch, enqueued behind a gate kernel so no host launch gap falls inside an interval; achieved = 2 x Linear "
-                           "MACs of those launches (reference flops.py accounting) / their summed device time; profile_ms_per_eval is the sum of all "
-                           "intervals per model evaluation (no programmatic-launch overlap between kernels: an event sits between them), "
-                           "timed_ms_per_eval the graph-replayed bench step / NFE"}
+                    "graph_span_ms_per_eval": None if span_ms is None else round(span_ms / prof_evals, 4),
+                    "how": prof_how + "; achieved = 2 x Linear MACs of the GEMM launches (reference flops.py accounting) / their summed device time; "
+                           "profile_ms_per_eval = sum of all kernel durations per model evaluation (kernels overlap slightly under programmatic "
+                           "launch, so the sum can exceed the span), timed_ms_per_eval = the timed bench step / NFE"}
         # --- parity of the benchmarked path (same model object, precision, batch, graph runner) against the fp32 CPU oracle, image 0
         try:
             O, o_model = oracle_model(wl, inner)

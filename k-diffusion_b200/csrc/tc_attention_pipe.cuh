@@ -27,15 +27,23 @@
 //            the 7 x 7 neighbourhood is a 128-bit mask per (row, block); 32-key chunks no row of the warp needs are skipped
 //   WINDOW : tile = one 8 x 8 window x 2 heads (rows = head-major); one key block; S is 128 x 128 with the two 64 x 64 diagonal
 //            blocks in use; the roll is TMA coordinates, the seam mask two 16-key groups per chunk
-// TMEM: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384).  Shared memory: Q 4 x 16 KiB, K/V 3 x 32 KiB, P 2 x 32 KiB = 224 KiB.
+// TMEM: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384).
+// P (the bf16 probabilities, A operand of the P V MMA) has two homes, template flag PT:
+//   PT = true  (default): P stays in TENSOR MEMORY.  The softmax thread packs two probabilities per 32-bit column and writes them
+//                with tcgen05.st over the first 64 columns of its own S tile (chunk c of P lands on columns the thread has already
+//                read), and the P V MMA takes its A operand from TMEM.  No shared-memory round trip, no proxy fence, and the
+//                64 KiB that P would need buy two more K/V stages: 5 x 32 KiB in flight instead of 3 -- the windowed modes consume
+//                one stage per tile and were bound by load latency with 3.
+//   PT = false (KDB200_ATTN_P_SMEM=1): P in shared memory (2 x 32 KiB, UMMA K-major SW128 layout), 3 K/V stages.
+// Shared memory: Q 4 x 16 KiB + K/V stages x 32 KiB (+ P 2 x 32 KiB) = 224 KiB either way.
 #pragma once
 
-constexpr int PA_STAGES = 3;
-constexpr size_t PA_SMEM = (size_t)(4 + 2 * PA_STAGES + 4) * TILE_BYTES + 1024 + 256;
+constexpr int PA_MAX_STAGES = 5;
+constexpr size_t PA_SMEM = (size_t)14 * TILE_BYTES + 1024 + 512;
 
 struct PipeAttnBars {
   uint64_t q_full[2], q_empty[2];
-  uint64_t kv_full[PA_STAGES], kv_empty[PA_STAGES];
+  uint64_t kv_full[PA_MAX_STAGES], kv_empty[PA_MAX_STAGES];
   uint64_t s_ready[2], p_ready[2], pv_done[2];
   uint32_t tmem;
 };
@@ -46,7 +54,18 @@ struct PipeAttnParams {
   int B, h, w, nh, shift;
   int nb;                  // key blocks per tile
   int n_pairs;             // tile pairs in total
+  long long* trace;        // debug (KDB200_ATTN_TRACE=1): [4 roles][PA_TRACE_N] (code, clock64) of CTA 0, else nullptr
 };
+constexpr int PA_TRACE_N = 192;
+// roles: 0 producer, 1 MMA issuer, 2 / 3 softmax group 0 / 1 (row 0 of the group)
+#define PA_TRACE(role_, code_)                                                                                     \
+  do {                                                                                                             \
+    if (p.trace != nullptr && blockIdx.x == 0 && tr_n < PA_TRACE_N) {                                              \
+      p.trace[((role_) * PA_TRACE_N + tr_n) * 2] = (code_);                                                        \
+      p.trace[((role_) * PA_TRACE_N + tr_n) * 2 + 1] = clock64();                                                  \
+      ++tr_n;                                                                                                      \
+    }                                                                                                              \
+  } while (0)
 
 struct PipeTile {          // decoded query tile
   int b, head;             // WINDOW: head = first head of the pair
@@ -87,17 +106,19 @@ __device__ __forceinline__ PipeTile pipe_decode(const PipeAttnParams& p, int pai
   return x;
 }
 
-template <int MODE>
+template <int MODE, bool PT>
 __global__ void __launch_bounds__(320, 1) attn_pipe_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_kv,
                                                            const PipeAttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   constexpr bool SHARED_KV = MODE == MODE_GLOBAL;
+  constexpr int PA_STAGES = PT ? 5 : 3;
+  int tr_n = 0;
   constexpr uint32_t KV_BYTES = (MODE == MODE_NA) ? NA_BLK_KEYS * 128 : TILE_BYTES;
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = base;                                   // [qbuf 2][tile 2] x 16 KiB
   uint8_t* sKV = sQ + 4 * TILE_BYTES;                   // [stage][K | V] x 16 KiB
   uint8_t* sP = sKV + 2 * PA_STAGES * TILE_BYTES;       // [tile 2][key half 2] x 16 KiB
-  PipeAttnBars* bars = reinterpret_cast<PipeAttnBars*>(sP + 4 * TILE_BYTES);
+  PipeAttnBars* bars = reinterpret_cast<PipeAttnBars*>(sP + (PT ? 0 : 4) * TILE_BYTES);      // 14 tiles either way
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nh = p.nh, nb = p.nb;
   const int n_local = (int)blockIdx.x < p.n_pairs ? (p.n_pairs - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -126,7 +147,7 @@ __global__ void __launch_bounds__(320, 1) attn_pipe_kernel(const __grid_constant
     }
     tc::fence_proxy_async();
   }
-  if constexpr (MODE == MODE_WINDOW) {
+  if constexpr (MODE == MODE_WINDOW && !PT) {
     // P of a window tile is block diagonal (rows of head 0 x keys of head 0, head 1 x head 1): the off-diagonal halves are zero for
     // every tile of this kernel -- written once here, never touched again
     if (warp < 8) {
@@ -167,6 +188,7 @@ __global__ void __launch_bounds__(320, 1) attn_pipe_kernel(const __grid_constant
       auto kv_stage = [&](const PipeTile& x, int j) {
         tc::mbar_wait(&bars->kv_empty[st], ph ^ 1u);
         tc::mbar_arrive_expect_tx(&bars->kv_full[st], 2 * KV_BYTES);
+        PA_TRACE(0, 100 + j);
         uint8_t* k = sKV + (size_t)(st * 2) * TILE_BYTES;
         if constexpr (MODE == MODE_GLOBAL) {
           tc::tma_load_3d(k, &tmap, &bars->kv_full[st], (nh + x.head) * DH, j * ROWS, x.b);
@@ -189,6 +211,7 @@ __global__ void __launch_bounds__(320, 1) attn_pipe_kernel(const __grid_constant
         const int qb = u & 1;
         tc::mbar_wait(&bars->q_empty[qb], (uint32_t)(((u >> 1) & 1) ^ 1));
         tc::mbar_arrive_expect_tx(&bars->q_full[qb], 2 * TILE_BYTES);
+        PA_TRACE(0, 1);
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           const PipeTile& x = t == 0 ? x0 : x1;
@@ -228,6 +251,7 @@ __global__ void __launch_bounds__(320, 1) attn_pipe_kernel(const __grid_constant
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k) tc::umma_bf16(tmem + (uint32_t)(t * 128), qd + 2ull * k, kd + 2ull * k, IDESC_S, (uint32_t)(k != 0));
         tc::umma_commit(&bars->s_ready[t]);
+        PA_TRACE(1, 10 + t);
       };
       for (int u = 0; u < n_local; ++u) {
         const int qb = u & 1;
@@ -240,6 +264,7 @@ __global__ void __launch_bounds__(320, 1) attn_pipe_kernel(const __grid_constant
           take(cs[1], cph[1]);
         }
         tc::mbar_wait(&bars->q_full[qb], (uint32_t)((u >> 1) & 1));
+        PA_TRACE(1, 2);
         // S tiles of the pair's first key block.  S_t is free: p_ready of the previous pair's last block was waited below.
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
@@ -262,14 +287,22 @@ __global__ void __launch_bounds__(320, 1) attn_pipe_kernel(const __grid_constant
           for (int t = 0; t < 2; ++t) {
             tc::mbar_wait(&bars->p_ready[t], n_p[t] & 1u);          // P_t(j) is in shared memory, S_t(j) fully read
             ++n_p[t];
+            PA_TRACE(1, 20 + t);
             // (O_t of the previous pair has left TMEM: the group reads it before it starts the tile whose P_t was just awaited)
             tc::tc_fence_after();
-            const uint64_t pd = tc::smem_desc_k_sw128(p_base + (uint32_t)(t * 2 * TILE_BYTES));
             const uint64_t vd = tc::smem_desc_mn_sw128(kv_base + (uint32_t)((cs[t] * 2 + 1) * TILE_BYTES), 1024, 1024);
+            if constexpr (PT) {        // A = P_t in TMEM: 8 columns (16 bf16) per k-step, over the first 64 columns of S_t
 #pragma unroll
-            for (int k = 0; k < ROWS / 16; ++k)
-              tc::umma_bf16(tmem + 256u + (uint32_t)(t * 64), pd + (uint64_t)((k >> 2) * (TILE_BYTES >> 4)) + 2ull * (k & 3),
-                            vd + (uint64_t)(k * ((16 * 128) >> 4)), IDESC_O, (uint32_t)((j | k) != 0));
+              for (int k = 0; k < ROWS / 16; ++k)
+                tc::umma_bf16_ts(tmem + 256u + (uint32_t)(t * 64), tmem + (uint32_t)(t * 128 + k * 8), vd + (uint64_t)(k * ((16 * 128) >> 4)), IDESC_O,
+                                 (uint32_t)((j | k) != 0));
+            } else {
+              const uint64_t pd = tc::smem_desc_k_sw128(p_base + (uint32_t)(t * 2 * TILE_BYTES));
+#pragma unroll
+              for (int k = 0; k < ROWS / 16; ++k)
+                tc::umma_bf16(tmem + 256u + (uint32_t)(t * 64), pd + (uint64_t)((k >> 2) * (TILE_BYTES >> 4)) + 2ull * (k & 3),
+                              vd + (uint64_t)(k * ((16 * 128) >> 4)), IDESC_O, (uint32_t)((j | k) != 0));
+            }
             tc::umma_commit(&bars->pv_done[t]);
             if (!SHARED_KV || t == 1) tc::umma_commit(&bars->kv_empty[cs[t]]);      // every MMA that reads this stage has been issued
             if (more) {                                                             // next block's S tile for the group that just finished
@@ -340,32 +373,43 @@ __global__ void __launch_bounds__(320, 1) attn_pipe_kernel(const __grid_constant
         }
         tc::mbar_wait(&bars->s_ready[t], n & 1u);
         tc::tc_fence_after();
+        if (row == 0) PA_TRACE(2 + t, 30);
+        // which of each chunk's 32 keys count for this row, and whether the warp needs the chunk at all (warp-uniform)
+        uint32_t mw[4];
+        bool need[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          // which of this chunk's 32 keys count for this row, and whether the warp needs the chunk at all (warp-uniform)
-          uint32_t mw = 0xffffffffu;
-          bool need = true;
+          mw[c] = 0xffffffffu;
+          need[c] = true;
           if constexpr (MODE == MODE_NA) {
-            mw = km[c];
-            need = __any_sync(0xffffffffu, mw != 0u);
+            mw[c] = km[c];
+            need[c] = __any_sync(0xffffffffu, mw[c] != 0u);
           } else if constexpr (MODE == MODE_WINDOW) {
-            need = (c >> 1) == hd;
-            mw = wmask[c & 1];
+            need[c] = (c >> 1) == hd;
+            mw[c] = wmask[c & 1];
           }
-          // (the P tile is free: s_ready of this block was committed after the previous block's P V MMAs, so they have completed)
-          if (MODE == MODE_WINDOW && !need) continue;        // off-diagonal half: zero since the prologue
+        }
+        // (the P tile is free: s_ready of this block was committed after the previous block's P V MMAs, so they have completed)
+        // S chunks are double buffered in registers: tcgen05.wait::ld waits for EVERY outstanding load, so the load of chunk c + 1
+        // is issued right after the wait for chunk c and streams in behind chunk c's exponentials
+        uint32_t r[2][32];
+        if (need[0]) tc::tmem_ld32_nowait(tmem_s, r[0]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (need[c]) tc::tmem_ld_wait(r[c & 1]);
+          if (c < 3 && need[c < 3 ? c + 1 : 3]) tc::tmem_ld32_nowait(tmem_s + (uint32_t)((c + 1) * 32), r[(c + 1) & 1]);
+          if (MODE == MODE_WINDOW && !PT && !need[c]) continue;        // off-diagonal half: zero since the prologue
           uint32_t pk[16];
-          if (need) {
-            uint32_t r[32];
-            tc::tmem_ld32_nowait(tmem_s + (uint32_t)(c * 32), r);
-            tc::tmem_ld_wait(r);
+          if (need[c]) {
+            const uint32_t* v = r[c & 1];
+            const uint32_t mwc = mw[c];
 #pragma unroll
             for (int i = 0; i < 16; i += 2) {
               float e[4];
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                e[q] = tc::ex2(fmaf(__uint_as_float(r[2 * i + q]), LOG2E, -mb));
-                if constexpr (MODE != MODE_GLOBAL) e[q] = (mw & (1u << (2 * i + q))) ? e[q] : 0.f;
+                e[q] = tc::ex2(fmaf(__uint_as_float(v[2 * i + q]), LOG2E, -mb));
+                if constexpr (MODE != MODE_GLOBAL) e[q] = (mwc & (1u << (2 * i + q))) ? e[q] : 0.f;
               }
               l0 += e[0];
               l1 += e[1];
@@ -378,14 +422,22 @@ __global__ void __launch_bounds__(320, 1) attn_pipe_kernel(const __grid_constant
 #pragma unroll
             for (int i = 0; i < 16; ++i) pk[i] = 0u;
           }
-          uint8_t* ph_ = pt + (c >> 1) * TILE_BYTES;
+          if constexpr (PT) {          // columns [16 c, 16 c + 16) of the own S tile: already read (chunk c covers columns up to 32 c + 31)
+            tc::tmem_st16(tmem_s + (uint32_t)(c * 16), pk);
+          } else {
+            uint8_t* ph_ = pt + (c >> 1) * TILE_BYTES;
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj)
-            *reinterpret_cast<uint4*>(ph_ + p_offset(row, (c & 1) * 4 + jj)) = make_uint4(pk[jj * 4], pk[jj * 4 + 1], pk[jj * 4 + 2], pk[jj * 4 + 3]);
+            for (int jj = 0; jj < 4; ++jj)
+              *reinterpret_cast<uint4*>(ph_ + p_offset(row, (c & 1) * 4 + jj)) = make_uint4(pk[jj * 4], pk[jj * 4 + 1], pk[jj * 4 + 2], pk[jj * 4 + 3]);
+          }
         }
-        tc::fence_proxy_async();
+        if constexpr (PT)
+          tc::tmem_st_wait();
+        else
+          tc::fence_proxy_async();
         tc::tc_fence_before();
         tc::mbar_arrive(&bars->p_ready[t]);
+        if (row == 0) PA_TRACE(2 + t, 31);
       }
       // ---- O_t / l -> out
       tc::mbar_wait(&bars->pv_done[t], (n - 1) & 1u);
@@ -396,6 +448,7 @@ __global__ void __launch_bounds__(320, 1) attn_pipe_kernel(const __grid_constant
       tc::tmem_ld_wait(o0);
       tc::tmem_ld_wait(o1);
       tc::tc_fence_before();
+      if (row == 0) PA_TRACE(2 + t, 32);
       const float inv = 1.f / ((l0 + l1) + (l2 + l3));
       int64_t token;
       int head = x.head;
@@ -439,18 +492,28 @@ __global__ void __launch_bounds__(320, 1) attn_pipe_kernel(const __grid_constant
   }
 }
 
-// host: launch the pipelined kernel when the geometry allows it (returns false -> caller falls back to the one-shot kernel)
-template <int MODE>
-static int launch_attn_pipe(const CUtensorMap& tq, const CUtensorMap& tkv, const PipeAttnParams& p, cudaStream_t st) {
+// host: launch the pipelined kernel
+template <int MODE, bool PT>
+static int launch_attn_pipe_impl(const CUtensorMap& tq, const CUtensorMap& tkv, PipeAttnParams p, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    KDB_CUDA(cudaFuncSetAttribute(attn_pipe_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PA_SMEM));
+    KDB_CUDA(cudaFuncSetAttribute(attn_pipe_kernel<MODE, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PA_SMEM));
     attr_set = true;
   }
   static const bool no_pdl = [] {
     const char* e_ = getenv("KDB200_NO_PDL");
     return e_ != nullptr && e_[0] == '1';
   }();
+  static const bool trace_on = [] {
+    const char* e_ = getenv("KDB200_ATTN_TRACE");
+    return e_ != nullptr && e_[0] == '1';
+  }();
+  static long long* trace_buf = nullptr;
+  if (trace_on) {
+    if (trace_buf == nullptr) KDB_CUDA(cudaMalloc(&trace_buf, 4 * PA_TRACE_N * 2 * sizeof(long long)));
+    KDB_CUDA(cudaMemsetAsync(trace_buf, 0, 4 * PA_TRACE_N * 2 * sizeof(long long), st));
+    p.trace = trace_buf;
+  }
   int sms = 0, dev = 0;
   KDB_CUDA(cudaGetDevice(&dev));
   KDB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -463,7 +526,33 @@ static int launch_attn_pipe(const CUtensorMap& tq, const CUtensorMap& tkv, const
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   lc.attrs = attr;
-  lc.numAttrs = no_pdl ? 0 : 1;
-  KDB_CUDA(cudaLaunchKernelEx(&lc, attn_pipe_kernel<MODE>, tq, tkv, p));
+  lc.numAttrs = no_pdl || trace_on ? 0 : 1;
+  KDB_CUDA(cudaLaunchKernelEx(&lc, attn_pipe_kernel<MODE, PT>, tq, tkv, p));
+  if (trace_on) {
+    static long long hbuf[4 * PA_TRACE_N * 2];
+    KDB_CUDA(cudaMemcpyAsync(hbuf, trace_buf, sizeof(hbuf), cudaMemcpyDeviceToHost, st));
+    KDB_CUDA(cudaStreamSynchronize(st));
+    long long t0 = 0;
+    for (int r = 0; r < 4; ++r)
+      if (hbuf[(r * PA_TRACE_N) * 2 + 1] != 0 && (t0 == 0 || hbuf[(r * PA_TRACE_N) * 2 + 1] < t0)) t0 = hbuf[(r * PA_TRACE_N) * 2 + 1];
+    fprintf(stderr, "ATTN trace MODE=%d PT=%d B=%d h=%d w=%d nh=%d nb=%d pairs=%d grid=%u (cycles since the first stamp of CTA 0; codes: 1 Q issue, 100+j K/V issue, 2 q_full, 10+t S issued, 20+t P ready seen, 30 S ready seen, 31 P written, 32 O read)\n",
+            MODE, (int)PT, p.B, p.h, p.w, p.nh, p.nb, p.n_pairs, lc.gridDim.x);
+    const char* names[4] = {"producer", "mma", "softmax0", "softmax1"};
+    for (int r = 0; r < 4; ++r) {
+      fprintf(stderr, " %-9s", names[r]);
+      for (int i = 0; i < PA_TRACE_N && hbuf[(r * PA_TRACE_N + i) * 2 + 1] != 0; ++i)
+        fprintf(stderr, " %lld@%lld", hbuf[(r * PA_TRACE_N + i) * 2], hbuf[(r * PA_TRACE_N + i) * 2 + 1] - t0);
+      fprintf(stderr, "\n");
+    }
+  }
   return 0;
+}
+
+template <int MODE>
+static int launch_attn_pipe(const CUtensorMap& tq, const CUtensorMap& tkv, const PipeAttnParams& p, cudaStream_t st) {
+  static const bool p_smem = [] {
+    const char* e_ = getenv("KDB200_ATTN_P_SMEM");
+    return e_ != nullptr && e_[0] == '1';
+  }();
+  return p_smem ? launch_attn_pipe_impl<MODE, false>(tq, tkv, p, st) : launch_attn_pipe_impl<MODE, true>(tq, tkv, p, st);
 }

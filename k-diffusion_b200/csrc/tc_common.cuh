@@ -171,6 +171,26 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[3
       : "r"(taddr)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (M = 128 rows = TMEM lanes, K along the columns, two bf16 per 32-bit column with the
+// even k in the low half) is read from tensor memory -- how P of attention reaches the P V MMA without a shared-memory round trip.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+// 32 lanes x 16 consecutive 32-bit columns, registers -> TMEM (thread i of the warp writes lane 32 * (warp % 4) + i)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+      "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // The same wait, with the destination registers of an earlier tmem_ld32_nowait tied to it as read-write operands: the compiler
 // then sees the values as PRODUCED here and cannot schedule their consumers above the wait (software-pipelined loops that keep
@@ -233,14 +253,16 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
   return d;
 }
-// value * gelu_fast(gate) for two (value, gate) pairs
-__device__ __forceinline__ f32x2 geglu2(f32x2 val, f32x2 gate) {
-  const f32x2 c1 = pk2(0.0356774081f, 0.0356774081f), c0 = pk2(0.7978845608f, 0.7978845608f), half = pk2(0.5f, 0.5f);
+// (2 * half_val) * gelu_fast(gate) for two (value, gate) pairs; `half_val` = 0.5 * value (the caller folds the 0.5 into the
+// row scale it applies anyway):  val * gate * (0.5 + 0.5 t) = w + w t  with w = half_val * gate  -> 5 packed instructions + 2 MUFU
+__device__ __forceinline__ f32x2 geglu2(f32x2 half_val, f32x2 gate) {
+  const f32x2 c1 = pk2(0.0356774081f, 0.0356774081f), c0 = pk2(0.7978845608f, 0.7978845608f);
   const f32x2 u = mul2(gate, fma2(c1, mul2(gate, gate), c0));
   float u0, u1;
   upk2(u, u0, u1);
   const f32x2 t = pk2(tanh_approx(u0), tanh_approx(u1));
-  return mul2(val, mul2(gate, fma2(half, t, half)));
+  const f32x2 w = mul2(half_val, gate);
+  return fma2(w, t, w);
 }
 
 // ---------------------------------------------------------------- descriptors

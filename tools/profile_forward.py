@@ -57,15 +57,21 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--json", default=None)
-    ap.add_argument("--config", default="sw", choices=["sw", "na"], help="sw = cfg2 shifted-window model, na = cfg3/4 neighbourhood model")
+    ap.add_argument("--config", default="sw", choices=["sw", "na", "c5"],
+                    help="sw = cfg2 shifted-window model, na = cfg3/4 neighbourhood model, c5 = cfg5 (512x512, widths 256/512/1024; use --batch 16)")
     ap.add_argument("--per-sample", action="store_true")
     ap.add_argument("--repeat", type=int, default=1, help="evaluations inside the profiled region")
     args = ap.parse_args()
     fixture = "cfg2_sw256_shapes.json" if args.config == "sw" else "cfg3_na256_config.json"
-    cfg = K.config.load_config(json.loads((ROOT / "tests/golden" / fixture).read_text())["config"])
+    raw = json.loads((ROOT / "tests/golden" / fixture).read_text())["config"]
+    if args.config == "c5":
+        raw = {"model": {"type": "image_transformer_v2", "input_channels": 3, "input_size": [512, 512], "patch_size": [4, 4],
+                         "depths": [2, 2, 4], "widths": [256, 512, 1024], "sigma_data": 0.5, "sigma_min": 1e-2, "sigma_max": 160}}
+    cfg = K.config.load_config(raw)
+    res = cfg["model"]["input_size"][0]
     inner = K.synth.synth_init_(K.config.make_model(cfg), seed=1).cuda().eval().set_precision(args.precision)
     model = K.Denoiser(inner, sigma_data=cfg["model"]["sigma_data"])
-    x = torch.randn(args.batch, 3, 256, 256, device="cuda") * 10
+    x = torch.randn(args.batch, 3, res, res, device="cuda") * 10
     sig = torch.full([args.batch], 3.0, device="cuda")
     eng = inner.engine()
     table = eng.conditioning(sig[:1])
