@@ -259,7 +259,17 @@ def graph_kernel_times(fn):
                 continue
             out.append((kernel_family(name), name, float(e.time_range.start), float(e.time_range.elapsed_us()) / 1000.0))
         out.sort(key=lambda r: r[2])
-        return out or None
+        # Under programmatic dependent launch a kernel is resident (prologue, then parked in griddepcontrol.wait) while its
+        # predecessor still runs, and CUPTI's duration includes that wait: the raw durations of one evaluation summed to 2.11 ms
+        # against a 1.69 ms span (profiles/r2_bench_cfg2_first.json).  Attribute to each kernel only the time after the previous
+        # kernel ENDED (one stream, in-order completion): the exclusive durations sum to the span exactly.
+        excl, prev_end = [], None
+        for fam, name, start, dur in out:
+            end = start + dur * 1000.0
+            lo = start if prev_end is None else max(start, min(prev_end, end))
+            excl.append((fam, name, start, (end - lo) / 1000.0))
+            prev_end = end if prev_end is None else max(prev_end, end)
+        return excl or None
     except Exception as exc:          # measurement aid only
         print(f"bench: torch.profiler unavailable ({exc!r}); falling back to CUDA events between eager launches", file=sys.stderr)
         return None
@@ -373,8 +383,9 @@ def main():
         recs = graph_kernel_times(lambda: run_sampler(x))
         if recs is not None:
             prof.launches = [(fam, ms_) for fam, _, _, ms_ in recs]
-            prof_evals, prof_how = NFE, ("CUPTI activity records (torch.profiler) of one replay of the timed CUDA graph: kernel durations "
-                                         "inside the graph, no events between kernels, no host launch gaps")
+            prof_evals, prof_how = NFE, ("CUPTI activity records (torch.profiler) of one replay of the timed CUDA graph, no events between kernels, "
+                                         "no host launch gaps; each kernel is charged the time from the END of its predecessor to its own end "
+                                         "(programmatic launch makes kernels resident early, so raw durations overlap and over-count)")
             span_ms = (recs[-1][2] + recs[-1][3] * 1000.0 - recs[0][2]) / 1000.0
         else:
             prof_steps = 5 if wl["sampler"] == "heun" else 9
@@ -450,8 +461,8 @@ def main():
                     "profile_ms_per_eval": round(total / prof_evals, 4), "timed_ms_per_eval": round(ms / args.steps / NFE, 4),
                     "graph_span_ms_per_eval": None if span_ms is None else round(span_ms / prof_evals, 4),
                     "how": prof_how + "; achieved = 2 x Linear MACs of the GEMM launches (reference flops.py accounting) / their summed device time; "
-                           "profile_ms_per_eval = sum of all kernel durations per model evaluation (kernels overlap slightly under programmatic "
-                           "launch, so the sum can exceed the span), timed_ms_per_eval = the timed bench step / NFE"}
+                           "profile_ms_per_eval = sum of the (exclusive) kernel times per model evaluation = graph span minus idle gaps, "
+                           "timed_ms_per_eval = the timed bench step / NFE"}
         # --- parity of the benchmarked path (same model object, precision, batch, graph runner) against the fp32 CPU oracle, image 0
         try:
             O, o_model = oracle_model(wl, inner)

@@ -1,15 +1,14 @@
-mkdir -p gpurun_out/r2b
-timeout 600 python -m pytest tests/test_gpu_tc.py -x -q -s 2>&1 | tail -25 > gpurun_out/r2b/pytest_tc.log
-echo "pytest_tc rc=$?" >> gpurun_out/r2b/pytest_tc.log
-if grep -q "failed\|error\|Error" gpurun_out/r2b/pytest_tc.log; then tail -30 gpurun_out/r2b/pytest_tc.log; exit 1; fi
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 > gpurun_out/r2b/pytest.log
-timeout 300 python __graft_entry__.py smoke > gpurun_out/r2b/smoke.log 2>&1
-timeout 400 python bench.py > gpurun_out/r2b/bench_cfg2.json 2> gpurun_out/r2b/bench_cfg2.err
-KDB200_ATTN_ONESHOT=1 timeout 200 python bench.py --no-extras > gpurun_out/r2b/bench_cfg2_oneshot.json 2> gpurun_out/r2b/bench_cfg2_oneshot.err
-timeout 400 python bench.py --config cfg3 > gpurun_out/r2b/bench_cfg3.json 2> gpurun_out/r2b/bench_cfg3.err
-timeout 200 python tools/profile_forward.py > gpurun_out/r2b/fwd_sw.txt 2>&1
-timeout 200 python tools/profile_forward.py --config na > gpurun_out/r2b/fwd_na.txt 2>&1
-timeout 200 python tools/profile_forward.py --config c5 --batch 16 > gpurun_out/r2b/fwd_c5.txt 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:attn_pipe --launch-skip 36 -c 12 -f -o gpurun_out/r2b/attn_sw python tools/profile_forward.py > gpurun_out/r2b/ncu_attn_sw.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:attn_pipe --launch-skip 36 -c 12 -f -o gpurun_out/r2b/attn_c5 python tools/profile_forward.py --config c5 --batch 16 > gpurun_out/r2b/ncu_attn_c5.log 2>&1
-tail -4 gpurun_out/r2b/pytest.log; tail -2 gpurun_out/r2b/smoke.log
+D=gpurun_out/r2d
+mkdir -p $D
+timeout 120 tools/bin/hw_probe > $D/hw_probe.txt 2>&1
+timeout 500 python bench.py --config cfg3 > $D/bench_cfg3.json 2> $D/bench_cfg3.err
+timeout 500 python bench.py --config cfg4 > $D/bench_cfg4.json 2> $D/bench_cfg4.err
+timeout 700 python bench.py --config cfg5 > $D/bench_cfg5.json 2> $D/bench_cfg5.err
+timeout 120 python tools/attn_trace.py > $D/attn_trace.txt 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:attn_pipe --launch-skip 36 -c 12 -f -o $D/attn_sw python tools/profile_forward.py > $D/ncu_attn_sw.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:attn_pipe --launch-skip 36 -c 12 -f -o $D/attn_c5 python tools/profile_forward.py --config c5 --batch 16 > $D/ncu_attn_c5.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:attn_pipe --launch-skip 36 -c 4 -f -o $D/attn_na python tools/profile_forward.py --config na > $D/ncu_attn_na.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_persist --launch-skip 156 -c 12 -f -o $D/gemm_sw python tools/profile_forward.py > $D/ncu_gemm_sw.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 204 -c 80 --csv --log-file $D/launches_sw.csv python tools/profile_forward.py > $D/ncu_ll_sw.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 204 -c 80 --csv --log-file $D/launches_c5.csv python tools/profile_forward.py --config c5 --batch 16 > $D/ncu_ll_c5.log 2>&1
+cat $D/hw_probe.txt; head -c 300 $D/bench_cfg5.json
