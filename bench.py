@@ -485,13 +485,15 @@ def main():
             budget = None
             bfile = ROOT / "tests" / "golden" / "bf16_budget.json"
             if bfile.exists() and args.precision == "bf16":
-                budget = json.loads(bfile.read_text()).get("cfg2_heun10", {}).get("rel_l2")
+                budget_key = "cfg5shape_sw_heun2" if args.config == "cfg5" else "cfg2_heun10"
+                budget = json.loads(bfile.read_text()).get(budget_key, {}).get("rel_l2")
             parity = {"rel_l2": float(d.norm() / want.double().norm()), "max_abs": float(d.abs().max()), "ref_rms": float(want.double().pow(2).mean().sqrt()),
                       "image": 0, "sampler_steps": p_steps, "of_steps": wl["steps"], "vs": "oracle/kdiff_oracle.py fp32 on the CPU, same weights / latent / schedule",
                       "path": f"{args.precision} token stream, fused RMSNorm, CUDA-graph replay, batch {B} (image 0 compared)",
                       "reference_own_bf16_rel_l2": budget,
                       "note": "reference_own_bf16_rel_l2 = distance of the reference under torch.autocast(bf16) from its own fp32 output "
-                              "(cfg2 model, Heun 10 steps; tests/golden/bf16_budget.json) -- the scale of a legitimate bf16 deviation"}
+                              "(tests/golden/bf16_budget.json: cfg2 model, Heun 10 steps; for cfg5 the 512x512 / 256-512-1024 shifted-window "
+                              "variant, Heun 2 steps) -- the scale of a legitimate bf16 deviation"}
         except Exception as exc:           # the parity leg must never cost the bench line
             parity = {"error": repr(exc)}
         if world == 1:

@@ -87,7 +87,8 @@ struct TcParams {
   int a_merge, mwc, mC;  // A operand gathered from fine tokens (TokenMerge): coarse grid width, fine channels
   int box_w, box_h;      // 5-D TMA boxes of merge / split: 128 rows = box_h x box_w coarse tokens
   long long* trace;      // debug: per-tile clock64 stamps of CTA 0 (KDB200_GEMM_TRACE=1), else nullptr
-  int dbg;               // experiments only (KDB200_GEMM_DBG bit mask, tools/gemm_probe.py): 1 = no staging stores / TMA store, 2 = no epilogue math, 4 = no tcgen05.ld
+  int dbg;               // experiments only (KDB200_GEMM_DBG bit mask, tools/gemm_probe.py): 8 = the MMA issuers do not wait for the accumulator, 16 = nor for A / B, 32 = no TMA loads
+                         // (bits 1 / 2 / 4 switched parts of the epilogue off for profiles/r2_gemm_probe_epilogue_knockout.txt and were removed again)
 };
 
 // fast erf-GELU: erf via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7, far below bf16 resolution)

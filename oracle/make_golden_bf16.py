@@ -9,7 +9,8 @@ reference module twice on identical inputs -- plain fp32 and under `torch.autoca
 distance between the two: that number is the reference's OWN bf16 noise, and the GPU tests allow the CUDA bf16 path a stated
 small multiple of it (tests/test_gpu_bf16_parity.py) instead of a hand-picked budget.
 
-Recorded for: sw64 (forward B=2 + Heun 6 steps), cfg2 256x256 (forward B=1, several sigmas; Heun 10 Karras steps B=1).
+Recorded for: sw64 (forward B=2 + Heun 6 steps), cfg2 256x256 (forward B=1, several sigmas; Heun 10 Karras steps B=1), and the
+cfg5 shape (512x512, widths 256/512/1024, shifted-window variant; Heun 2 steps B=1).
 Latents and solver arithmetic stay fp32 in both runs (as in the reference's demo()/sample paths under accelerate).
 """
 import json
@@ -71,6 +72,14 @@ def main():
         out[f"cfg2_forward_sigma{s}"] = both(lambda: model(xs, torch.tensor([s])))
     sig10 = S.get_sigmas_karras(10, 1e-2, 160)
     out["cfg2_heun10"] = both(lambda: S.sample_heun(model, x, sig10, disable=True))
+    # cfg5 shape (512x512, widths 256/512/1024), Heun 2 Karras steps, B=1: what bench.py's parity leg can afford on the CPU for cfg5.
+    # The reference cannot run its neighbourhood layers here (natten is absent), so this is the shifted-window variant of the same
+    # widths / depths / resolution: same GEMM shapes and accumulation lengths, i.e. the same bf16 noise sources.
+    model = build(dict(input_size=[512, 512], widths=[256, 512, 1024], depths=[2, 2, 4]))
+    g = torch.Generator().manual_seed(126)
+    x = torch.randn(1, 3, 512, 512, generator=g) * 160
+    sig2 = S.get_sigmas_karras(2, 1e-2, 160)
+    out["cfg5shape_sw_heun2"] = both(lambda: S.sample_heun(model, x, sig2, disable=True))
     (G.OUT / "bf16_budget.json").write_text(json.dumps(out, indent=1))
     print(json.dumps(out, indent=1))
 

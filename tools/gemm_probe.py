@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """What bounds the persistent tcgen05 GEMM?  Times the GEGLU and plain-store kernels at the cfg2 level shapes with parts of the epilogue
-switched off (KDB200_GEMM_DBG, read per launch): 1 = no staging st.shared / TMA store, 2 = no epilogue math, 4 = no tcgen05.ld.
+switched off (KDB200_GEMM_DBG, read per launch): 8 = the MMA issuers do not wait for the accumulator, 16 = nor for A / B, 32 = no TMA loads.
+(Bits 1 / 2 / 4 = no staging stores / no epilogue math / no tcgen05.ld existed for profiles/r2_gemm_probe_epilogue_knockout.txt and were removed from the kernel.)
 GPU box:  python tools/gemm_probe.py  [--trace]"""
 import os
 import sys
@@ -29,9 +30,9 @@ def timed(fn, reps=20):
     return e0.elapsed_time(e1) / reps * 1e3
 
 
-MODES = [int(v) for v in os.environ.get("PROBE_MODES", "0,1,2,4,7,15,23,31,63").split(",")]
+MODES = [int(v) for v in os.environ.get("PROBE_MODES", "0,8,24,56").split(",")]
 SHAPES = [(131072, 768, 128), (32768, 1536, 256), (8192, 3072, 512)] if os.environ.get("PROBE_ALL_SHAPES", "1") == "1" else [(131072, 768, 128), (32768, 1536, 256)]
-print("KDB200_GEMM_MAX_NB =", os.environ.get("KDB200_GEMM_MAX_NB"), " modes: 1 no staging/TMA store, 2 no math, 4 no tcgen05.ld, 8 MMA does not wait for the accumulator, "
+print("KDB200_GEMM_MAX_NB =", os.environ.get("KDB200_GEMM_MAX_NB"), " modes: 8 MMA does not wait for the accumulator, "
       "16 MMA does not wait for A/B, 32 no TMA loads at all")
 for (M, N2, K) in SHAPES:
     a = torch.randn(M, K, device="cuda").to(torch.bfloat16)

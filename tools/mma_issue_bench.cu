@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(384, 1) issue_rate(int tiles, int vary, int co
         case 1: tc::fence_proxy_async(); break;                                                   // generic -> async proxy fence
         case 2: tc::mbar_try_wait(&never_bar, 0); break;                                           // parked mbarrier wait (suspend hint)
         case 3: tc::tc_fence_before(); tc::tc_fence_after(); break;
-        case 4: tc::named_barrier_sync(1 + ((warp - 4) >> 2), 128); break;                         // two groups of 4 warps
+        case 4: __syncwarp(); break;                                                                // (bar.sync would deadlock at the stop flag)
         case 5: {                                                                                  // st.shared + proxy fence + bulk store + wait (the epilogue's tail)
           *reinterpret_cast<uint4*>(scratch + (threadIdx.x & 31) * 16) = make_uint4(1, 2, 3, 4);
           tc::fence_proxy_async();
@@ -138,6 +138,7 @@ void run(int vary, int commit, int a_tmem, long long* dout, int noise = 0) {
   printf("noise=%-32s N=%3d A=%s vary=%d commit=%d: %6.1f cycles per MMA (issue loop alone %6.1f) -> %5.0f FLOP/clk/SM  [%s]\n",
          nn[noise], N, a_tmem ? "tmem" : "smem", vary, commit, (double)h[0] / (8.0 * tiles), (double)h[1] / (8.0 * tiles), 2.0 * 128 * N * 16 * 8.0 * tiles / h[0], cudaGetErrorString(e));
   (void)nn;
+  fflush(stdout);
 }
 
 int main() {
