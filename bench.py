@@ -230,7 +230,7 @@ def kernel_family(name):
     name = name.replace("(int)", "").replace(" ", "")
     if "gemm_tc_kernel<64,5>" in name:
         return "patch_out"
-    for key, fam in (("gemm_tc", "gemm_tc"), ("gemm_simt", "gemm_simt"), ("attn_", "attn_tc"), ("patch_in", "patch_in"), ("patch_out", "patch_out"),
+    for key, fam in (("ffn_fused", "gemm_tc"), ("gemm_tc", "gemm_tc"), ("gemm_simt", "gemm_simt"), ("attn_", "attn_tc"), ("patch_in", "patch_in"), ("patch_out", "patch_out"),
                      ("fold_norm", "fused_norm"), ("ew_kernel", "solver"), ("precond", "precond"), ("noise_", "noise"),
                      ("conditioning", "cond"), ("rmsnorm", "rmsnorm"), ("qknorm", "qknorm_rope"), ("geglu_kernel", "geglu")):
         if key in name:
@@ -410,16 +410,17 @@ def main():
         # Launches are matched to shapes by execution order (k_diffusion.models.flops.linear_layers).
         gemm_fams = [f for f in prof.by_family if f.startswith("gemm")]
         g_times = [t for f, t in prof.launches if f.startswith("gemm")]
-        seq = K.models.flops.linear_layers(cfg["model"], B)
+        fused_ffn = os.environ.get("KDB200_NO_FFN_FUSE", "0") != "1"
+        seq = K.models.flops.launch_layers(cfg["model"], B, fused_ffn)
         per_shape, per_level = {}, {}
         for idx, t in enumerate(g_times):
-            label, M_, N_, K_ = seq[idx % len(seq)]
-            key = (label.split(" ", 1)[-1] if " " in label else label.rstrip("0123456789"), M_, N_, K_)
+            label, M_, N_, K_, macs_ = seq[idx % len(seq)]
+            key = (label.split(" ", 1)[-1] if " " in label else label.rstrip("0123456789"), M_, N_, K_, macs_)
             c, tot = per_shape.get(key, (0, 0.0))
             per_shape[key] = (c + 1, tot + t)
             lvl = label[:2] if label.startswith("L") else ("mid" if label.startswith("mid") else "merge/split")
             fl, tt = per_level.get(lvl, (0.0, 0.0))
-            per_level[lvl] = (fl + 2.0 * M_ * N_ * K_, tt + t)
+            per_level[lvl] = (fl + 2.0 * macs_, tt + t)
         g_launch, g_ms = len(g_times), sum(g_times)
         flops = 2.0 * K.models.flops.linear_macs(cfg["model"], B) * (len(g_times) / len(seq))
         peaks_file = ROOT / "MEASURED_PEAKS.json"
@@ -429,8 +430,8 @@ def main():
             peak, which = 1400.0, "fallback (B200_PROFILING.md sustained 1.4 PFLOP/s)"
         ach = flops / (g_ms / 1000.0) / 1e12
         shapes = []
-        for (kind, M_, N_, K_), (c, tot) in sorted(per_shape.items(), key=lambda kv: -kv[1][1])[:8]:
-            tf = 2.0 * M_ * N_ * K_ * c / (tot / 1000.0) / 1e12
+        for (kind, M_, N_, K_, macs_), (c, tot) in sorted(per_shape.items(), key=lambda kv: -kv[1][1])[:8]:
+            tf = 2.0 * macs_ * c / (tot / 1000.0) / 1e12
             shapes.append({"op": kind, "M": M_, "N": N_, "K": K_, "launches": c, "avg_launch_us": round(1000.0 * tot / c, 2),
                            "achieved": round(tf, 1), "frac": round(tf / peak, 4), "share_of_step": round(tot / total, 4)})
         by_level = {lvl: {"achieved": round(fl / (tt / 1000.0) / 1e12, 1), "frac": round(fl / (tt / 1000.0) / 1e12 / peak, 4),

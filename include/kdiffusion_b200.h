@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define KDB_ABI_VERSION 4
+#define KDB_ABI_VERSION 5
 
 #define KDB_ERR_BAD_ARG      (-1)
 #define KDB_ERR_UNSUPPORTED  (-2)
@@ -200,6 +200,14 @@ int kdb_gemm_bf16(const void* a_bf16, const void* w_bf16, void* c_bf16, int M, i
  * (rows g*8 .. g*8+7 of the first half) followed by the 8 matching gate rows (second half).  ss_in (may be NULL): [M, 8] fp32
  * sum(x^2) per 128-channel block of A's rows; the epilogue then scales the accumulator by 1/rms (fused RMSNorm). */
 int kdb_gemm_bf16_geglu(const void* a_bf16, const void* w_il_bf16, void* c_bf16, int M, int N2, int K, const float* ss_in, void* stream);
+
+/* The whole feed-forward block of a 128-wide level in one kernel, IN PLACE on the raw residual stream x[M,128] (bf16):
+ *   x <- x + down_proj( value(x_n) * gelu(gate(x_n)) ),  x_n = x / rms(x)      (image_transformer_v2.py:479-493, :89-95; the AdaRMSNorm
+ * channel scale is expected folded into w_up_il's columns).  w_up_il [2*d_ff,128] row-interleaved as for kdb_gemm_bf16_geglu,
+ * w_down [128,d_ff]; ss_in [M,8] fp32 with sum(x^2) of each row in slot 0 (required), ss_out (may be NULL, may alias ss_in) receives
+ * sum(x_new^2).  Needs M % 128 == 0, d_ff % 64 == 0, d_ff >= 192.  The [M,d_ff] hidden never leaves the SM. */
+int kdb_ffn_fused_bf16(void* x_bf16, const void* w_up_il_bf16, const void* w_down_bf16, int M, int d_ff, const float* ss_in, float* ss_out,
+                       void* stream);
 
 /* out[B,h,w,nh*e] = attention(qkv[B,h,w,3*nh*e]) on fp32 or bf16 token tensors, feature order
  * (t nh e) as produced by qkv_proj (image_transformer_v2.py:377,386,422,431,467). q/k must already be

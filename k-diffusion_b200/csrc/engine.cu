@@ -397,6 +397,13 @@ int run_layer(KdbModel* m, const LayerPlan& L, T* x, int B, int h, int w, const 
     if ((rc = linear<T>(ao, WSel<T>::out(L), x, M, C, C, e, st))) return rc;
     if ((rc = tap<T>(m, tag + ".attn", x, M * C, st))) return rc;
   }
+  // fused feed-forward (128-wide levels): the hidden never leaves the SM.  Not when the hidden itself is being tapped.
+  if (fold && m->ss_valid && L.up_wf != nullptr && L.down_wb != nullptr && tc_ffn_fused_supported(M, C, L.dff) &&
+      !(m->tap_out != nullptr && m->tap_name == tag + ".geglu")) {
+    if ((rc = launch_ffn_fused(reinterpret_cast<bf16*>(x), L.up_wf, L.down_wb, M, C, L.dff, ws.rowss, ws.rowss, st))) return rc;
+    m->ss_valid = true;
+    return tap<T>(m, tag + ".ff", x, M * C, st);
+  }
   bool fused_geglu = false;
   if (fold && m->ss_valid && L.up_wf != nullptr && tc_gemm_geglu_supported(M, 2 * L.dff, C, true)) {
     if ((rc = launch_gemm_tc_geglu(reinterpret_cast<const bf16*>(x), L.up_wf, reinterpret_cast<bf16*>(gb), M, 2 * L.dff, C, st, ws.rowss))) return rc;

@@ -390,6 +390,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
 }
 
 #include "tc_gemm_persist.cuh"
+#include "tc_ffn_fused.cuh"
 
 bool use_persistent(const TcParams& p) {
   static const bool off = [] {
@@ -804,6 +805,19 @@ int launch_gemm_tc_geglu(const bf16* A, const bf16* W_il, bf16* out, int64_t M, 
   return launch_tc<128, TCE_GEGLU>(A, W_il, p, st);
 }
 
+bool tc_ffn_fused_supported(int64_t M, int C, int dff) {
+  static const bool off = [] {
+    const char* e = getenv("KDB200_NO_FFN_FUSE");
+    return e != nullptr && e[0] == '1';
+  }();
+  return !off && !g_tc_disabled && ffn_fused_supported(M, C, dff);
+}
+
+int launch_ffn_fused(bf16* x, const bf16* w_up_il, const bf16* w_down, int64_t M, int C, int dff, const float* ss_in, float* ss_out, cudaStream_t st) {
+  KDB_REQUIRE(ffn_fused_supported(M, C, dff) && ss_in != nullptr, KDB_ERR_BAD_SHAPE, "ffn_fused: unsupported shape (needs C = 128, M %% 128 == 0, d_ff %% 64 == 0)");
+  return launch_ffn_fused_impl(x, w_up_il, w_down, M, dff, ss_in, ss_out, st);
+}
+
 }  // namespace kdb
 
 extern "C" int kdb_gemm_bf16(const void* a, const void* w, void* c, int M, int N, int K, void* stream) {
@@ -820,4 +834,11 @@ extern "C" int kdb_gemm_bf16_geglu(const void* a, const void* w_il, void* c, int
   KDB_REQUIRE(tc_gemm_geglu_supported(M, N2, K, ss_in != nullptr), KDB_ERR_UNSUPPORTED,
               "gemm_bf16_geglu: needs N2 %% 128 == 0 and K %% 64 == 0 (K %% 128 == 0, K <= 1024 with ss_in); got M=%d N2=%d K=%d", M, N2, K);
   return launch_gemm_tc_geglu(static_cast<const bf16*>(a), static_cast<const bf16*>(w_il), static_cast<bf16*>(c), M, N2, K, (cudaStream_t)stream, ss_in);
+}
+
+extern "C" int kdb_ffn_fused_bf16(void* x, const void* w_up_il, const void* w_down, int M, int d_ff, const float* ss_in, float* ss_out, void* stream) {
+  using namespace kdb;
+  KDB_REQUIRE(x && w_up_il && w_down && ss_in, KDB_ERR_BAD_ARG, "ffn_fused_bf16: NULL operand");
+  return launch_ffn_fused(static_cast<bf16*>(x), static_cast<const bf16*>(w_up_il), static_cast<const bf16*>(w_down), M, 128, d_ff, ss_in, ss_out,
+                          (cudaStream_t)stream);
 }

@@ -16,6 +16,12 @@ int launch_gemm_tc(const bf16* A, const bf16* W, bf16* C, int64_t M, int N, int 
 bool tc_gemm_geglu_supported(int64_t M, int N2, int K, bool fused_norm = false);
 int launch_gemm_tc_geglu(const bf16* A, const bf16* W_il, bf16* out, int64_t M, int N2, int K, cudaStream_t st, const float* ss_in = nullptr);
 
+// The whole feed-forward block of a 128-wide level in one kernel (tc_ffn_fused.cuh): x <- x + down(value(x_n) * gelu(gate(x_n))), in place.
+// w_up_il carries the AdaRMSNorm channel scale (fold kernel) and the value / gate row interleave; ss_in = row statistics of x (required),
+// ss_out = where to leave sum(x_new^2) per row (or nullptr).  KDB200_NO_FFN_FUSE=1 disables it (the two stand-alone GEMMs run instead).
+bool tc_ffn_fused_supported(int64_t M, int C, int dff);
+int launch_ffn_fused(bf16* x, const bf16* w_up_il, const bf16* w_down, int64_t M, int C, int dff, const float* ss_in, float* ss_out, cudaStream_t st);
+
 // W'[n,k] = W[n,k] * g[k] for a table of weight matrices (AdaRMSNorm channel scale folded into the consumer weights)
 struct FoldDesc {
   const bf16* src;

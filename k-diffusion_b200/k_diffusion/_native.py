@@ -17,7 +17,7 @@ LIB_PATH = Path(os.environ.get("KDB200_LIB", _HERE / "_lib" / "libkdb200.so"))
 PREC_FP32, PREC_BF16 = 0, 1
 ATTN_NONE, ATTN_GLOBAL, ATTN_NEIGHBORHOOD, ATTN_SHIFTED_WINDOW = 0, 1, 2, 3
 MAX_LEVELS = 8
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 _vp, _i32, _i64, _f32, _f64, _u64, _sz = (ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double,
                                            ctypes.c_uint64, ctypes.c_size_t)
@@ -63,6 +63,7 @@ SIGNATURES = {
     "kdb_model_tap_count": (_i64, [_vp]),
     "kdb_gemm_bf16": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "kdb_gemm_bf16_geglu": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "kdb_ffn_fused_bf16": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "kdb_attention": (_i32, [_i32, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
 }
 
@@ -436,6 +437,18 @@ def gemm_bf16_geglu(a, w_up, ss_in=None):
     out = torch.empty(M, N2 // 2, dtype=torch.bfloat16, device=a.device)
     check(lib().kdb_gemm_bf16_geglu(ptr(a), ptr(w_il), ptr(out), M, N2, K, ptr(ss_in), stream()))
     return out
+
+
+@_on_device_of_first
+def ffn_fused_bf16(x, w_up, w_down, ss_in, ss_out=None):
+    """x [M,128] bf16 (updated IN PLACE and returned), w_up [2F,128] bf16 (reference row order), w_down [128,F] bf16, ss_in [M,8] fp32 with
+    sum(x^2) per row in slot 0: x <- x + (value * gelu(gate))(x / rms(x)) @ w_down^T in one kernel (tc_ffn_fused.cuh)."""
+    require_cuda(x, w_up, w_down, ss_in, ss_out)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and w_down.is_contiguous() and ss_in.dtype == torch.float32
+    M, F = x.shape[0], w_down.shape[1]
+    w_il = interleave_geglu_rows(w_up)
+    check(lib().kdb_ffn_fused_bf16(ptr(x), ptr(w_il), ptr(w_down), M, F, ptr(ss_in), ptr(ss_out), stream()))
+    return x
 
 
 @_on_device_of_first

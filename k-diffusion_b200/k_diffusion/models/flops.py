@@ -38,6 +38,25 @@ def linear_layers(mcfg, batch=1):
     return seq
 
 
+FUSED_FFN_WIDTHS = (128,)      # level widths whose feed-forward block runs as ONE kernel (csrc/tc_ffn_fused.cuh)
+
+
+def launch_layers(mcfg, batch=1, fused_ffn=True):
+    """[(label, M, N, K, macs)] per tensor-core GEMM LAUNCH in execution order: like `linear_layers`, but an up_proj + down_proj pair of a
+    128-wide level is one launch when the fused feed-forward kernel is active (N, K are then the up projection's; macs covers both)."""
+    out, seq, i = [], linear_layers(mcfg, batch), 0
+    while i < len(seq):
+        label, M, N, K = seq[i]
+        if fused_ffn and label.endswith("up+geglu") and K in FUSED_FFN_WIDTHS and i + 1 < len(seq):
+            _, M2, N2, K2 = seq[i + 1]
+            out.append((label.replace("up+geglu", "ffn (up+geglu+down+res, fused)"), M, N, K, M * N * K + M2 * N2 * K2))
+            i += 2
+        else:
+            out.append((label, M, N, K, M * N * K))
+            i += 1
+    return out
+
+
 def linear_macs(mcfg, batch=1):
     return sum(M * N * K for _, M, N, K in linear_layers(mcfg, batch))
 

@@ -111,3 +111,39 @@ def test_attention_generic_fp32_exact():
         want = _ref_attention(qkv, h, w, 2, kind, param, shift)
         got = N_.attention(qkv, h, w, 2, 64, kind, param, shift).cpu()
         assert float((got - want).abs().max()) < 2e-5, kind
+
+
+@pytest.mark.parametrize("M,F", [(128, 192), (1280, 384), (148 * 128 * 2 + 384, 384), (131072, 384), (4096, 512)])
+def test_ffn_fused_matches_reference_and_unfused_kernels(M, F):
+    """tc_ffn_fused.cuh: x <- x + (value * gelu(gate))(x / rms) @ Wdown^T in one kernel, against (a) an fp32 torch reference of the same
+    op and (b) the two stand-alone tensor-core kernels it replaces (within bf16 rounding of the output)."""
+    from k_diffusion import _native as N_
+    g = torch.Generator(device=DEV).manual_seed(M + F)
+    C = 128
+    x = (torch.randn(M, C, device=DEV, generator=g) * (0.5 + torch.rand(M, 1, device=DEV, generator=g) * 3)).to(torch.bfloat16)
+    w_up = (torch.randn(2 * F, C, device=DEV, generator=g) / C ** 0.5).to(torch.bfloat16)
+    w_dn = (torch.randn(C, F, device=DEV, generator=g) / F ** 0.5).to(torch.bfloat16)
+    ss = torch.zeros(M, 8, device=DEV)
+    ss[:, 0] = x.float().pow(2).sum(1)
+    ss[:, 1:] = float("nan")                   # only slot 0 belongs to a 128-wide level: the others must never be read
+    # (b) the stand-alone kernels
+    h = N_.gemm_bf16_geglu(x, w_up, ss_in=ss)
+    y_unfused = (x.float() + N_.gemm_bf16(h, w_dn).float()).to(torch.bfloat16)
+    # (a) fp32 reference, hidden rounded to bf16 where the kernels round it
+    xn = x.float() * torch.rsqrt(ss[:, :1] / C + 1e-6)
+    u = xn @ w_up.float().T
+    hid = (u[:, :F] * torch.nn.functional.gelu(u[:, F:])).to(torch.bfloat16).float()
+    want = x.float() + hid @ w_dn.float().T
+    ss_out = torch.full((M, 8), -1.0, device=DEV)
+    got = N_.ffn_fused_bf16(x.clone(), w_up, w_dn, ss, ss_out)
+    torch.cuda.synchronize()
+    err = (got.float() - want).abs()
+    tol = 1.5e-2 * want.abs() + 3e-2
+    assert bool((err <= tol).all()), f"vs fp32 reference: max err {float(err.max()):.4f} (want {float(want.flatten()[err.argmax()]):.4f})"
+    d = (got.float() - y_unfused.float()).abs()
+    # (the stand-alone pair rounds the down projection to bf16 before the residual add, the fused kernel adds in fp32: one-ulp differences)
+    assert bool((d <= 2 ** -6 * (want.abs() + 1.0)).all()), f"vs stand-alone kernels: max |diff| {float(d.max()):.4g}"
+    # row statistics of the new stream for the next fused RMSNorm: slot 0 only
+    want_ss = got.float().pow(2).sum(1)
+    assert torch.allclose(ss_out[:, 0], want_ss, rtol=2e-2, atol=1e-2)
+    assert bool((ss_out[:, 1:] == -1.0).all())

@@ -87,7 +87,9 @@ def main():
     with _native.profile(gate_ms=10.0 * args.repeat) as prof:
         for _ in range(args.repeat):
             evaluate()
-    seq = gemm_sequence(cfg["model"], args.batch)
+    import os
+    seq = [(lab, M, N, Kd) for lab, M, N, Kd, _ in K.models.flops.launch_layers(cfg["model"], args.batch, os.environ.get("KDB200_NO_FFN_FUSE", "0") != "1")]
+    macs = {i: m for i, (_, _, _, _, m) in enumerate(K.models.flops.launch_layers(cfg["model"], args.batch, os.environ.get("KDB200_NO_FFN_FUSE", "0") != "1"))}
     gi = 0
     rows = []
     peak = 1396.9
@@ -95,8 +97,8 @@ def main():
         note = ""
         if fam.startswith("gemm"):
             label, M, N, Kd = seq[gi % len(seq)]
+            tf = 2.0 * macs[gi % len(seq)] / (ms * 1e-3) / 1e12
             gi += 1
-            tf = 2.0 * M * N * Kd / (ms * 1e-3) / 1e12
             gb = 2.0 * (M * Kd + N * Kd + M * (N if "geglu" not in label else N // 2) + (M * N if "res" in label else 0)) / (ms * 1e-3) / 1e9
             note = f"{label:18s} M={M:6d} N={N:5d} K={Kd:5d}  {tf:7.1f} TFLOP/s ({tf / peak:5.1%})  min-traffic {gb:7.0f} GB/s"
         rows.append((fam, ms, note))
