@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(352, 1) attn_pipe_kernel(const __grid_constant
           }
       };
       auto kv_stage = [&](const PipeTile& x, int j) {
-        tc::mbar_wait(&bars->kv_empty[st], ph ^ 1u);
+        tc::mbar_wait_role(&bars->kv_empty[st], ph ^ 1u);
         tc::mbar_arrive_expect_tx(&bars->kv_full[st], 2 * KV_BYTES);
         PA_TRACE(0, 100 + j);
         uint8_t* k = sKV + (size_t)(st * 2) * TILE_BYTES;
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(352, 1) attn_pipe_kernel(const __grid_constant
         const int pair = (int)blockIdx.x + u * (int)gridDim.x;
         const PipeTile x0 = pipe_decode<MODE>(p, pair, 0), x1 = pipe_decode<MODE>(p, pair, 1);
         const int qb = u & 1;
-        tc::mbar_wait(&bars->q_empty[qb], (uint32_t)(((u >> 1) & 1) ^ 1));
+        tc::mbar_wait_role(&bars->q_empty[qb], (uint32_t)(((u >> 1) & 1) ^ 1));
         tc::mbar_arrive_expect_tx(&bars->q_full[qb], 2 * TILE_BYTES);
         PA_TRACE(0, 1);
 #pragma unroll
@@ -268,16 +268,16 @@ __global__ void __launch_bounds__(352, 1) attn_pipe_kernel(const __grid_constant
         const int qb = u & 1;
         uint32_t cs, cph, ns = 0, nph = 0;
         take(cs, cph);
-        tc::mbar_wait(&bars->q_full[qb], (uint32_t)((u >> 1) & 1));
+        tc::mbar_wait_role(&bars->q_full[qb], (uint32_t)((u >> 1) & 1));
         if (t == 0) PA_TRACE(1, 2);
         // S tile of the pair's first key block.  S_t is free: p_ready of the previous pair's last block was waited below.
-        tc::mbar_wait(&bars->kv_full[cs], cph);
+        tc::mbar_wait_role(&bars->kv_full[cs], cph);
         tc::tc_fence_after();
         issue_s(qb, cs);
         for (int j = 0; j < nb; ++j) {
           const bool more = j + 1 < nb;
           if (more) take(ns, nph);
-          tc::mbar_wait(&bars->p_ready[t], n_p & 1u);          // P_t(j) is written, S_t(j) fully read
+          tc::mbar_wait_role(&bars->p_ready[t], n_p & 1u);          // P_t(j) is written, S_t(j) fully read
           ++n_p;
           if (t == 0) PA_TRACE(1, 20);
           // (O_t of the previous pair has left TMEM: the group reads it before it starts the tile whose P_t was just awaited)
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(352, 1) attn_pipe_kernel(const __grid_constant
           tc::umma_commit(&bars->pv_done[t]);
           tc::umma_commit(&bars->kv_empty[cs]);                  // every MMA of THIS issuer that reads the stage has been issued
           if (more) {                                             // next block's S tile
-            tc::mbar_wait(&bars->kv_full[ns], nph);
+            tc::mbar_wait_role(&bars->kv_full[ns], nph);
             tc::tc_fence_after();
             issue_s(qb, ns);
           }

@@ -44,11 +44,19 @@ struct FfnBars {
 };
 constexpr size_t FF_SMEM = (size_t)FF_XBUF * FF_X_BYTES + (size_t)FF_WU * FF_WU_BYTES + (size_t)FF_WD * FF_WD_BYTES + sizeof(FfnBars) + 1024;
 
+constexpr int FF_TRACE_Q = 30;
+#define FF_TRACE(q_, slot_)                                                                         \
+  do {                                                                                             \
+    if (p.trace != nullptr && blockIdx.x == 0 && (q_) < FF_TRACE_Q) p.trace[(q_) * 8 + (slot_)] = clock64(); \
+  } while (0)
+
 struct FfnParams {
   const float* ss_in;      // [M, SS_PARTS] sum(x^2) of the input rows (slot 0 = the 128 channels)
   float* ss_out;           // same for the output rows, or nullptr
   int64_t M;               // tokens, multiple of 128
   int nc;                  // d_ff / 64 chunks, >= 3
+  long long* trace;        // KDB200_FFN_TRACE=1: clock64 stamps of CTA 0, [FF_TRACE_Q chunks][8 slots], else nullptr
+  int dbg;                 // experiments (KDB200_FFN_DBG, tools/ffn_probe.py; results are garbage): 1 = weights are loaded for the first tile only, 2 = no GEGLU arithmetic
 };
 
 __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmwu,
@@ -106,7 +114,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const __grid_c
       uint32_t su = 0, pu = 0, sd = 0, pd = 0;        // ring slot / phase of the next Wup / Wdown chunk
       auto load_x = [&](int i) {
         const int buf = i & 1;
-        tc::mbar_wait(&bars->x_empty[buf], (uint32_t)(((i >> 1) & 1) ^ 1));
+        tc::mbar_wait_role(&bars->x_empty[buf], (uint32_t)(((i >> 1) & 1) ^ 1));
         tc::mbar_arrive_expect_tx(&bars->x_full[buf], FF_X_BYTES);
         const int m0 = ((int)blockIdx.x + i * (int)gridDim.x) * BM;
         tc::tma_load_2d(sX + (size_t)buf * FF_X_BYTES, &tmx, &bars->x_full[buf], 0, m0);
@@ -115,17 +123,25 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const __grid_c
       if (n_local > 0) load_x(0);
       for (int i = 0; i < n_local; ++i) {
         for (int c = 0; c < nc; ++c) {
-          tc::mbar_wait(&bars->wu_empty[su], pu ^ 1u);
-          tc::mbar_arrive_expect_tx(&bars->wu_full[su], FF_WU_BYTES);
-          tc::tma_load_2d(sWU + (size_t)su * FF_WU_BYTES, &tmwu, &bars->wu_full[su], 0, c * 128);
-          tc::tma_load_2d(sWU + (size_t)su * FF_WU_BYTES + A_STAGE_BYTES, &tmwu, &bars->wu_full[su], BK, c * 128);
+          tc::mbar_wait_role(&bars->wu_empty[su], pu ^ 1u);
+          if ((p.dbg & 1) && i > 0) {
+            tc::mbar_arrive(&bars->wu_full[su]);
+          } else {
+            tc::mbar_arrive_expect_tx(&bars->wu_full[su], FF_WU_BYTES);
+            tc::tma_load_2d(sWU + (size_t)su * FF_WU_BYTES, &tmwu, &bars->wu_full[su], 0, c * 128);
+            tc::tma_load_2d(sWU + (size_t)su * FF_WU_BYTES + A_STAGE_BYTES, &tmwu, &bars->wu_full[su], BK, c * 128);
+          }
           if (++su == FF_WU) {
             su = 0;
             pu ^= 1u;
           }
-          tc::mbar_wait(&bars->wd_empty[sd], pd ^ 1u);
-          tc::mbar_arrive_expect_tx(&bars->wd_full[sd], FF_WD_BYTES);
-          tc::tma_load_2d(sWD + (size_t)sd * FF_WD_BYTES, &tmwd, &bars->wd_full[sd], c * FF_CH, 0);
+          tc::mbar_wait_role(&bars->wd_empty[sd], pd ^ 1u);
+          if ((p.dbg & 1) && i > 0) {
+            tc::mbar_arrive(&bars->wd_full[sd]);
+          } else {
+            tc::mbar_arrive_expect_tx(&bars->wd_full[sd], FF_WD_BYTES);
+            tc::tma_load_2d(sWD + (size_t)sd * FF_WD_BYTES, &tmwd, &bars->wd_full[sd], c * FF_CH, 0);
+          }
           if (++sd == FF_WD) {
             sd = 0;
             pd ^= 1u;
@@ -137,37 +153,59 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const __grid_c
     }
   } else if (pwarp == 13) {
     // ------------------------------------------------------------------ M1 issuer: acc1[b] = X . Wup_c^T
-    if (tc::elect_one()) {
+    // The waits of chunk q + 1 (accumulator buffer free, weights landed, next X tile landed) are taken BETWEEN the two k-blocks of chunk
+    // q: the first four MMAs are executing then, so the ~100 cycles each wait costs even when its phase is long complete (and the
+    // bookkeeping) are hidden instead of idling the tensor pipe (role trace profiles/r2_ffn_fused_role_trace_before.txt: 930 cycles
+    // per chunk for 512 cycles of M1 work).  None of those barriers can depend on chunk q itself (they are fed by chunk q - 2 or older).
+    if (tc::elect_one() && n_local > 0) {
       constexpr uint32_t IDESC = tc::idesc_bf16(BM, 128);
       const uint32_t x_base = tc::smem_u32(sX), wu_base = tc::smem_u32(sWU);
       uint32_t su = 0, pu = 0;
-      uint32_t b = 0, u_par = 1;       // acc1 buffer of the next chunk (q % 3) and the parity of its "free" wait: ((q / 3) & 1) ^ 1
+      uint32_t b = 0, u_par = 1;       // acc1 buffer of the current chunk (q % 3) and the parity of its "free" wait: ((q / 3) & 1) ^ 1
+      // waits of the very first chunk
+      tc::mbar_wait_role(&bars->x_full[0], 0);
+      tc::mbar_wait_role(&bars->acc1_free[0], 1);
+      tc::mbar_wait_role(&bars->wu_full[0], 0);
       for (int i = 0; i < n_local; ++i) {
-        const int buf = i & 1;
-        tc::mbar_wait(&bars->x_full[buf], (uint32_t)((i >> 1) & 1));
-        const uint32_t xa = x_base + (uint32_t)(buf * FF_X_BYTES);
+        const uint32_t xa = x_base + (uint32_t)((i & 1) * FF_X_BYTES);
         for (int c = 0; c < nc; ++c) {
-          tc::mbar_wait(&bars->acc1_free[b], u_par);          // M2 of the chunk that used this buffer before has completed (first use: passes)
-          tc::mbar_wait(&bars->wu_full[su], pu);
           tc::tc_fence_after();
+          FF_TRACE(i * nc + c, 0);
           const uint32_t d = tm_acc1 + b * 128u;
           const uint32_t wa = wu_base + su * (uint32_t)FF_WU_BYTES;
+          {
+            const uint64_t ad = tc::smem_desc_k_sw128(xa), bd = tc::smem_desc_k_sw128(wa);
 #pragma unroll
-          for (int kb = 0; kb < 2; ++kb) {
-            const uint64_t ad = tc::smem_desc_k_sw128(xa + (uint32_t)(kb * A_STAGE_BYTES)), bd = tc::smem_desc_k_sw128(wa + (uint32_t)(kb * A_STAGE_BYTES));
+            for (int k = 0; k < 4; ++k) tc::umma_bf16(d, ad + 2ull * k, bd + 2ull * k, IDESC, (uint32_t)(k != 0));
+          }
+          // next chunk's state and waits
+          uint32_t nsu = su + 1, npu = pu, nb_ = b + 1, nu_par = u_par;
+          if (nsu == FF_WU) {
+            nsu = 0;
+            npu ^= 1u;
+          }
+          if (nb_ == FF_NG) {
+            nb_ = 0;
+            nu_par ^= 1u;
+          }
+          const bool next_tile = c + 1 == nc;
+          if (!(next_tile && i + 1 == n_local)) {
+            if (next_tile) tc::mbar_wait_role(&bars->x_full[(i + 1) & 1], (uint32_t)(((i + 1) >> 1) & 1));
+            tc::mbar_wait_role(&bars->acc1_free[nb_], nu_par);      // M2 of the chunk that used that buffer before has completed (first use: passes)
+            tc::mbar_wait_role(&bars->wu_full[nsu], npu);
+          }
+          {
+            const uint64_t ad = tc::smem_desc_k_sw128(xa + (uint32_t)A_STAGE_BYTES), bd = tc::smem_desc_k_sw128(wa + (uint32_t)A_STAGE_BYTES);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) tc::umma_bf16(d, ad + 2ull * k, bd + 2ull * k, IDESC, (uint32_t)((kb | k) != 0));
+            for (int k = 0; k < 4; ++k) tc::umma_bf16(d, ad + 2ull * k, bd + 2ull * k, IDESC, 1u);
           }
           tc::umma_commit(&bars->acc1_full[b]);
           tc::umma_commit(&bars->wu_empty[su]);
-          if (++su == FF_WU) {
-            su = 0;
-            pu ^= 1u;
-          }
-          if (++b == FF_NG) {
-            b = 0;
-            u_par ^= 1u;
-          }
+          FF_TRACE(i * nc + c, 1);
+          su = nsu;
+          pu = npu;
+          b = nb_;
+          u_par = nu_par;
         }
       }
     }
@@ -179,17 +217,19 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const __grid_c
       uint32_t sd = 0, pd = 0;
       uint32_t b = 0, u_par = 0;       // h_ready[b] parity of the next chunk: (q / 3) & 1
       for (int i = 0; i < n_local; ++i) {
-        tc::mbar_wait(&bars->acc2_free, (uint32_t)((i & 1) ^ 1));        // the previous tile's final epilogue has read acc2 (first tile: passes)
+        tc::mbar_wait_role(&bars->acc2_free, (uint32_t)((i & 1) ^ 1));        // the previous tile's final epilogue has read acc2 (first tile: passes)
         for (int c = 0; c < nc; ++c) {
-          tc::mbar_wait(&bars->wd_full[sd], pd);
-          tc::mbar_wait(&bars->h_ready[b], u_par);
+          tc::mbar_wait_role(&bars->wd_full[sd], pd);
+          tc::mbar_wait_role(&bars->h_ready[b], u_par);
           tc::tc_fence_after();
+          FF_TRACE(i * nc + c, 2);
           const uint64_t bd = tc::smem_desc_k_sw128(wd_base + sd * (uint32_t)FF_WD_BYTES);
           const uint32_t a = tm_acc1 + b * 128u;                         // H_c: 32 columns of packed bf16 pairs
 #pragma unroll
           for (int k = 0; k < 4; ++k) tc::umma_bf16_ts(tm_acc2, a + (uint32_t)(k * 8), bd + 2ull * k, IDESC, (uint32_t)((c | k) != 0));
           tc::umma_commit(&bars->acc1_free[b]);
           tc::umma_commit(&bars->wd_empty[sd]);
+          FF_TRACE(i * nc + c, 3);
           if (++sd == FF_WD) {
             sd = 0;
             pd ^= 1u;
@@ -218,57 +258,64 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const __grid_c
     uint32_t use = 0;                        // uses of acc1[grp] so far = q / 3
     float rstd = 1.f;
     int rstd_tile = -1;
+    int pending_buf = -1;                    // (issuer thread) X buffer whose output store has been issued but not yet drained
     while (i < n_local) {
       const int64_t m = ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * BM + row;
       if (rstd_tile != i) {                  // 1/rms of this thread's row: once per tile (two chunks per tile and group at d_ff = 384)
         rstd = rsqrtf(__ldg(p.ss_in + m * SS_PARTS) / (float)FF_C + 1e-6f);
         rstd_tile = i;
       }
-      tc::mbar_wait(&bars->acc1_full[grp], use & 1u);
+      tc::mbar_wait_group(&bars->acc1_full[grp], use & 1u);
       tc::tc_fence_after();
       ++use;
+      if (row == 0) FF_TRACE(i * nc + c, 4);
       const tc::f32x2 r2 = tc::pk2(rstd, rstd), rh = tc::pk2(0.5f * rstd, 0.5f * rstd);     // the GELU's 0.5 rides on the value's row scale
+      // four sub-passes of 32 accumulator columns = two [8 value | 8 gate] groups = 16 hidden features = 8 packed H columns.  The loads
+      // are double buffered in registers: tcgen05.wait::ld waits for every outstanding load, so the load of sub-pass s + 1 is issued right
+      // after the wait for sub-pass s and streams in behind its arithmetic (a load + wait costs ~250 cycles when nothing hides it).
+      uint32_t rr[2][32];
+      tc::tmem_ld32_nowait(tm_mine, rr[0]);
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        float v[64];
-        {
-          uint32_t r0[32], r1[32];
-          tc::tmem_ld32_nowait(tm_mine + (uint32_t)(g * 64), r0);
-          tc::tmem_ld32_nowait(tm_mine + (uint32_t)(g * 64 + 32), r1);
-          tc::tmem_ld_wait();
+      for (int sp = 0; sp < 4; ++sp) {
+        tc::tmem_ld_wait(rr[sp & 1]);
+        if (sp < 3) tc::tmem_ld32_nowait(tm_mine + (uint32_t)((sp + 1) * 32), rr[(sp + 1) & 1]);
+        const uint32_t* v = rr[sp & 1];
+        uint32_t pk[8];
 #pragma unroll
-          for (int t = 0; t < 32; ++t) { v[t] = __uint_as_float(r0[t]); v[32 + t] = __uint_as_float(r1[t]); }
-        }
-        // columns come as [8 value | 8 gate] groups (interleaved up_proj rows); feature pair (2j, 2j+1) of group gg -> one 32-bit column of H
-        uint32_t pk[16];
-#pragma unroll
-        for (int gg = 0; gg < 4; ++gg) {
+        for (int gg = 0; gg < 2; ++gg) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            tc::f32x2 val = tc::pk2(v[gg * 16 + 2 * j], v[gg * 16 + 2 * j + 1]);
-            tc::f32x2 gate = tc::pk2(v[gg * 16 + 8 + 2 * j], v[gg * 16 + 8 + 2 * j + 1]);
+            tc::f32x2 val = tc::pk2(__uint_as_float(v[gg * 16 + 2 * j]), __uint_as_float(v[gg * 16 + 2 * j + 1]));
+            tc::f32x2 gate = tc::pk2(__uint_as_float(v[gg * 16 + 8 + 2 * j]), __uint_as_float(v[gg * 16 + 8 + 2 * j + 1]));
             val = tc::mul2(val, rh);
             gate = tc::mul2(gate, r2);
             float o0, o1;
-            tc::upk2(tc::geglu2(val, gate), o0, o1);
+            tc::upk2((p.dbg & 2) ? val : tc::geglu2(val, gate), o0, o1);
             pk[gg * 4 + j] = tc::pack_bf16x2(o0, o1);
           }
         }
-        // H columns [16 g, 16 g + 16) overwrite accumulator columns this thread has already read (pass 1 reads columns 64..127)
-        tc::tmem_st16(tm_mine + (uint32_t)(g * 16), pk);
+        // H columns [8 sp, 8 sp + 8) overwrite accumulator columns this thread has already read (sub-pass s covers columns up to 32 s + 31)
+        tc::tmem_st8(tm_mine + (uint32_t)(sp * 8), pk);
       }
       tc::tmem_st_wait();
       tc::tc_fence_before();
       tc::mbar_arrive(&bars->h_ready[grp]);
+      if (row == 0) FF_TRACE(i * nc + c, 5);
+      if (issuer && pending_buf >= 0) {      // the output store issued one chunk ago has long finished reading the X buffer
+        tc::tma_store_wait_read();
+        tc::mbar_arrive(&bars->x_empty[pending_buf]);      // tile + 2 may load into it
+        pending_buf = -1;
+      }
 
       const bool last_of_tile = c + FF_NG >= nc;
       if (last_of_tile && (i % FF_NG) == grp) {
         // ---- final epilogue of tile i: out = acc2 + x (residual from the X tile in shared memory), in place, then TMA store
         const int buf = i & 1;
         uint8_t* xt = sX + (size_t)buf * FF_X_BYTES;
-        tc::mbar_wait(&bars->acc2_full[grp], (uint32_t)((i / FF_NG) & 1));
+        tc::mbar_wait_group(&bars->acc2_full[grp], (uint32_t)((i / FF_NG) & 1));
         tc::tc_fence_after();
-        tc::mbar_wait(&bars->x_full[buf], (uint32_t)((i >> 1) & 1));     // long complete (the MMAs consumed the tile): acquire for the residual reads below
+        if (row == 0) FF_TRACE(i * nc + c, 6);
+        tc::mbar_wait_group(&bars->x_full[buf], (uint32_t)((i >> 1) & 1));     // long complete (the MMAs consumed the tile): acquire for the residual reads below
 
         float ssq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -318,8 +365,8 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const __grid_c
           tc::tma_store_2d(&tmo, xt, 0, m0);
           tc::tma_store_2d(&tmo, xt + SUB_TILE_BYTES, 64, m0);
           tc::tma_store_commit();
-          tc::tma_store_wait_read();         // the X buffer may be refilled (tile i + 2)
-          tc::mbar_arrive(&bars->x_empty[buf]);
+          pending_buf = buf;                 // drained after this group's NEXT chunk: the wait sat on every tile boundary's critical path
+          FF_TRACE(i * nc + c, 7);
         }
       }
       c += FF_NG;
@@ -328,6 +375,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const __grid_c
         ++i;
       }
     }
+    if (issuer && pending_buf >= 0) tc::tma_store_wait_read();
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -357,7 +405,18 @@ int launch_ffn_fused_impl(bf16* x, const bf16* w_up_il, const bf16* w_down, int6
     const char* e = getenv("KDB200_NO_PDL");
     return e != nullptr && e[0] == '1';
   }();
-  FfnParams p{ss_in, ss_out, M, dff / FF_CH};
+  const char* dbg_env = getenv("KDB200_FFN_DBG");      // read per launch: tools/ffn_probe.py flips it between timed runs
+  FfnParams p{ss_in, ss_out, M, dff / FF_CH, nullptr, dbg_env != nullptr ? atoi(dbg_env) : 0};
+  static const bool trace_on = [] {
+    const char* e = getenv("KDB200_FFN_TRACE");
+    return e != nullptr && e[0] == '1';
+  }();
+  static long long* trace_buf = nullptr;
+  if (trace_on) {
+    if (trace_buf == nullptr) KDB_CUDA(cudaMalloc(&trace_buf, FF_TRACE_Q * 8 * sizeof(long long)));
+    KDB_CUDA(cudaMemsetAsync(trace_buf, 0, FF_TRACE_Q * 8 * sizeof(long long), st));
+    p.trace = trace_buf;
+  }
   const int64_t m_tiles = M / BM;
   cudaLaunchConfig_t lc{};
   lc.gridDim = dim3((unsigned)(m_tiles < num_sms() ? m_tiles : num_sms()));
@@ -371,5 +430,18 @@ int launch_ffn_fused_impl(bf16* x, const bf16* w_up_il, const bf16* w_down, int6
   lc.numAttrs = no_pdl ? 0 : 1;
   KDB_CUDA(cudaLaunchKernelEx(&lc, ffn_fused_kernel, tx, twu, twd, to, p));
   KDB_LAUNCH_CHECK(F_GEMM_TC, st);
+  if (trace_on) {
+    static long long h[FF_TRACE_Q * 8];
+    KDB_CUDA(cudaMemcpyAsync(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost, st));
+    KDB_CUDA(cudaStreamSynchronize(st));
+    fprintf(stderr, "FFN trace M=%lld nc=%d grid=%u (CTA 0, cycles since M1 of chunk 0 was ready to issue): q: M1 waits done / M1 issued+committed | M2 waits done / M2 issued | group saw acc1_full / arrived h_ready | final epilogue saw acc2_full / store drained\n",
+            (long long)M, p.nc, lc.gridDim.x);
+    const long long t0 = h[0];
+    for (int q = 0; q < FF_TRACE_Q; ++q) {
+      fprintf(stderr, " q %2d:", q);
+      for (int k = 0; k < 8; ++k) fprintf(stderr, " %lld", h[q * 8 + k] ? h[q * 8 + k] - t0 : -1);
+      fprintf(stderr, "\n");
+    }
+  }
   return 0;
 }

@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(persist_threads<EPI>(), 1) gemm_tc_persist(con
         int m0, n0, j;
         coords(it, m0, n0, j);
         for (int kb = 0; kb < nkb; ++kb) {
-          tc::mbar_wait(&bars->empty[s], ph ^ 1u);
+          tc::mbar_wait_role(&bars->empty[s], ph ^ 1u);
           tc::mbar_arrive_expect_tx(&bars->full[s], (uint32_t)stage_bytes);
           uint8_t* a = sStage + (size_t)s * stage_bytes;
           if (p.a_merge) {   // TokenMerge: k-block kb lives in quadrant (nh, nw) of the fine grid, channels e0..e0+63
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(persist_threads<EPI>(), 1) gemm_tc_persist(con
     // the waits themselves (~110 cycles each even when the phase is already complete) still overlap the other issuer's MMAs.
     const int id = warp - 1, n_iss = cfg.issuers;
     if (id < n_iss && tc::elect_one()) {
-      if (cfg.b_res && n_local > 0) tc::mbar_wait(&bars->b_full, 0);
+      if (cfg.b_res && n_local > 0) tc::mbar_wait_role(&bars->b_full, 0);
       const bool wait_acc = !(p.dbg & 8), wait_ab = !(p.dbg & (16 | 32));     // experiments (tools/gemm_probe.py): results are garbage
       const uint32_t stage_base = tc::smem_u32(sStage), b_base = tc::smem_u32(sB);
       const uint32_t n_stages = (uint32_t)cfg.stages, sbytes = (uint32_t)stage_bytes;
@@ -223,10 +223,10 @@ __global__ void __launch_bounds__(persist_threads<EPI>(), 1) gemm_tc_persist(con
       for (uint32_t it = (uint32_t)id; it < (uint32_t)n_local; it += (uint32_t)n_iss) {
         KDB_TRACE(1);
         if (n_iss == 2) {
-          tc::mbar_wait(&bars->turn[id], turn_par);
+          tc::mbar_wait_role(&bars->turn[id], turn_par);
           turn_par ^= 1u;
         }
-        if (wait_acc) tc::mbar_wait(&bars->tmem_empty[acc], acc_par);     // epilogue drained it
+        if (wait_acc) tc::mbar_wait_role(&bars->tmem_empty[acc], acc_par);     // epilogue drained it
         tc::tc_fence_after();
         KDB_TRACE(2);
         const uint32_t d = tmem + acc * P_BN;
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(persist_threads<EPI>(), 1) gemm_tc_persist(con
         for (int kb = 0; kb < nkb; kb += 2) {
           const bool two = kb + 1 < nkb;
           const uint32_t sa = ss, aa0 = aa, bb0 = bb;
-          if (first && wait_ab) tc::mbar_wait(&bars->full[sa], pp);
+          if (first && wait_ab) tc::mbar_wait_role(&bars->full[sa], pp);
           if (first && kb == 0) KDB_TRACE(13);
           aa += sbytes;
           bb += bres ? (uint32_t)P_B_TILE_BYTES : sbytes;
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(persist_threads<EPI>(), 1) gemm_tc_persist(con
           }
           const uint32_t sb = ss, aa1 = aa, bb1 = bb;
           if (two) {
-            if (first && wait_ab) tc::mbar_wait(&bars->full[sb], pp);
+            if (first && wait_ab) tc::mbar_wait_role(&bars->full[sb], pp);
             aa += sbytes;
             bb += bres ? (uint32_t)P_B_TILE_BYTES : sbytes;
             if (++ss == n_stages) {
