@@ -153,59 +153,39 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const __grid_c
     }
   } else if (pwarp == 13) {
     // ------------------------------------------------------------------ M1 issuer: acc1[b] = X . Wup_c^T
-    // The waits of chunk q + 1 (accumulator buffer free, weights landed, next X tile landed) are taken BETWEEN the two k-blocks of chunk
-    // q: the first four MMAs are executing then, so the ~100 cycles each wait costs even when its phase is long complete (and the
-    // bookkeeping) are hidden instead of idling the tensor pipe (role trace profiles/r2_ffn_fused_role_trace_before.txt: 930 cycles
-    // per chunk for 512 cycles of M1 work).  None of those barriers can depend on chunk q itself (they are fed by chunk q - 2 or older).
-    if (tc::elect_one() && n_local > 0) {
+    if (tc::elect_one()) {
       constexpr uint32_t IDESC = tc::idesc_bf16(BM, 128);
       const uint32_t x_base = tc::smem_u32(sX), wu_base = tc::smem_u32(sWU);
       uint32_t su = 0, pu = 0;
-      uint32_t b = 0, u_par = 1;       // acc1 buffer of the current chunk (q % 3) and the parity of its "free" wait: ((q / 3) & 1) ^ 1
-      // waits of the very first chunk
-      tc::mbar_wait_role(&bars->x_full[0], 0);
-      tc::mbar_wait_role(&bars->acc1_free[0], 1);
-      tc::mbar_wait_role(&bars->wu_full[0], 0);
+      uint32_t b = 0, u_par = 1;       // acc1 buffer of the next chunk (q % 3) and the parity of its "free" wait: ((q / 3) & 1) ^ 1
       for (int i = 0; i < n_local; ++i) {
-        const uint32_t xa = x_base + (uint32_t)((i & 1) * FF_X_BYTES);
+        const int buf = i & 1;
+        tc::mbar_wait_role(&bars->x_full[buf], (uint32_t)((i >> 1) & 1));
+        const uint32_t xa = x_base + (uint32_t)(buf * FF_X_BYTES);
         for (int c = 0; c < nc; ++c) {
+          tc::mbar_wait_role(&bars->acc1_free[b], u_par);          // M2 of the chunk that used this buffer before has completed (first use: passes)
+          tc::mbar_wait_role(&bars->wu_full[su], pu);
           tc::tc_fence_after();
           FF_TRACE(i * nc + c, 0);
           const uint32_t d = tm_acc1 + b * 128u;
           const uint32_t wa = wu_base + su * (uint32_t)FF_WU_BYTES;
-          {
-            const uint64_t ad = tc::smem_desc_k_sw128(xa), bd = tc::smem_desc_k_sw128(wa);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) tc::umma_bf16(d, ad + 2ull * k, bd + 2ull * k, IDESC, (uint32_t)(k != 0));
-          }
-          // next chunk's state and waits
-          uint32_t nsu = su + 1, npu = pu, nb_ = b + 1, nu_par = u_par;
-          if (nsu == FF_WU) {
-            nsu = 0;
-            npu ^= 1u;
-          }
-          if (nb_ == FF_NG) {
-            nb_ = 0;
-            nu_par ^= 1u;
-          }
-          const bool next_tile = c + 1 == nc;
-          if (!(next_tile && i + 1 == n_local)) {
-            if (next_tile) tc::mbar_wait_role(&bars->x_full[(i + 1) & 1], (uint32_t)(((i + 1) >> 1) & 1));
-            tc::mbar_wait_role(&bars->acc1_free[nb_], nu_par);      // M2 of the chunk that used that buffer before has completed (first use: passes)
-            tc::mbar_wait_role(&bars->wu_full[nsu], npu);
-          }
-          {
-            const uint64_t ad = tc::smem_desc_k_sw128(xa + (uint32_t)A_STAGE_BYTES), bd = tc::smem_desc_k_sw128(wa + (uint32_t)A_STAGE_BYTES);
+          for (int kb = 0; kb < 2; ++kb) {
+            const uint64_t ad = tc::smem_desc_k_sw128(xa + (uint32_t)(kb * A_STAGE_BYTES)), bd = tc::smem_desc_k_sw128(wa + (uint32_t)(kb * A_STAGE_BYTES));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) tc::umma_bf16(d, ad + 2ull * k, bd + 2ull * k, IDESC, 1u);
+            for (int k = 0; k < 4; ++k) tc::umma_bf16(d, ad + 2ull * k, bd + 2ull * k, IDESC, (uint32_t)((kb | k) != 0));
           }
           tc::umma_commit(&bars->acc1_full[b]);
           tc::umma_commit(&bars->wu_empty[su]);
           FF_TRACE(i * nc + c, 1);
-          su = nsu;
-          pu = npu;
-          b = nb_;
-          u_par = nu_par;
+          if (++su == FF_WU) {
+            su = 0;
+            pu ^= 1u;
+          }
+          if (++b == FF_NG) {
+            b = 0;
+            u_par ^= 1u;
+          }
         }
       }
     }
@@ -258,7 +238,6 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const __grid_c
     uint32_t use = 0;                        // uses of acc1[grp] so far = q / 3
     float rstd = 1.f;
     int rstd_tile = -1;
-    int pending_buf = -1;                    // (issuer thread) X buffer whose output store has been issued but not yet drained
     while (i < n_local) {
       const int64_t m = ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * BM + row;
       if (rstd_tile != i) {                  // 1/rms of this thread's row: once per tile (two chunks per tile and group at d_ff = 384)
@@ -301,11 +280,6 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const __grid_c
       tc::tc_fence_before();
       tc::mbar_arrive(&bars->h_ready[grp]);
       if (row == 0) FF_TRACE(i * nc + c, 5);
-      if (issuer && pending_buf >= 0) {      // the output store issued one chunk ago has long finished reading the X buffer
-        tc::tma_store_wait_read();
-        tc::mbar_arrive(&bars->x_empty[pending_buf]);      // tile + 2 may load into it
-        pending_buf = -1;
-      }
 
       const bool last_of_tile = c + FF_NG >= nc;
       if (last_of_tile && (i % FF_NG) == grp) {
@@ -365,7 +339,8 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const __grid_c
           tc::tma_store_2d(&tmo, xt, 0, m0);
           tc::tma_store_2d(&tmo, xt + SUB_TILE_BYTES, 64, m0);
           tc::tma_store_commit();
-          pending_buf = buf;                 // drained after this group's NEXT chunk: the wait sat on every tile boundary's critical path
+          tc::tma_store_wait_read();         // the X buffer may be refilled (tile i + 2)
+          tc::mbar_arrive(&bars->x_empty[buf]);
           FF_TRACE(i * nc + c, 7);
         }
       }
@@ -375,7 +350,6 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const __grid_c
         ++i;
       }
     }
-    if (issuer && pending_buf >= 0) tc::tma_store_wait_read();
   }
   tc::tc_fence_before();
   __syncthreads();
