@@ -448,7 +448,11 @@ def main():
         if ncu_file.exists():
             try:
                 first = json.loads(ncu_file.read_text())["roofline_kernel"]
-                traffic = (float(first["dram__bytes_read.sum [Mbyte]"]) + float(first["dram__bytes_write.sum [Mbyte]"])) * 1e6
+                unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                traffic = 0.0
+                for key, val in first.items():          # ncu picks the unit per value: "dram__bytes_read.sum [Mbyte]", "... [Kbyte]"
+                    if key.startswith("dram__bytes_read.sum [") or key.startswith("dram__bytes_write.sum ["):
+                        traffic += float(val) * unit[key[key.index("[") + 1:-1]]
                 traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the heaviest shape (" + first["launch"] +
                                 "), from the committed ncu --set full capture profiles/r2_ncu_full_summary.json")
             except (KeyError, ValueError, StopIteration):

@@ -205,3 +205,28 @@ def test_cfg_wrapper_against_reference_closure():
     assert_close(fn(z["x"], c["sigma"], class_cond=c["class_cond"]), c["model_fn"], what="cfg model_fn")
     got = O.sample_dpmpp_2m_sde(fn, z["x"], z["sigmas"], noise_sampler=None, extra_args=dict(class_cond=c["class_cond"]), eta=0.0, solver_type="heun")
     assert_close(got, c["dpmpp_2m_sde_heun_eta0"], what="cfg dpmpp_2m_sde")
+
+
+DPM_ADAPTIVE_CASES = {"dpm_adaptive_o3": dict(), "dpm_adaptive_o2": dict(order=2), "dpm_adaptive_o3_tight": dict(rtol=0.01, atol=0.002, h_init=0.1),
+                      "dpm_adaptive_o3_pid": dict(pcoeff=0.2, icoeff=0.7, dcoeff=0.1, accept_safety=0.9), "dpm_adaptive_o3_eta05": dict(eta=0.5, s_noise=0.9)}
+
+
+def test_dpm_solver_fast_and_adaptive_against_reference():
+    """DPM-Solver fast (every order pattern) and adaptive 12 / 23 with the PID controller, bit-identical to
+    the outputs oracle/make_golden_dpm.py recorded from the reference (sampling.py:303-516), step / rejection counts included."""
+    z = load_npz("toy_dpm_solvers.npz")
+    toy2 = lambda x, s, **kw: x / (1 + s[:, None, None, None] ** 2) + 0.1 * torch.tanh(x)
+    x = z["x"]
+
+    def ns():
+        it = iter(z["noise"])
+        return lambda a, b: next(it)
+
+    for n in (4, 5, 6, 9, 10):
+        assert torch.equal(O.sample_dpm_fast(toy2, x, 1e-2, 80., n), z[f"dpm_fast_n{n}"]), n
+    assert torch.equal(O.sample_dpm_fast(toy2, x, 1e-2, 80., 7, eta=0.5, s_noise=0.9, noise_sampler=ns()), z["dpm_fast_n7_eta05"])
+    assert torch.equal(O.sample_dpm_fast(toy2, x, 1e-2, 80., 6, eta=1.0, noise_sampler=ns()), z["dpm_fast_n6_eta1"])
+    for name, kw in DPM_ADAPTIVE_CASES.items():
+        got, info = O.sample_dpm_adaptive(toy2, x, 1e-2, 80., noise_sampler=ns() if kw.get("eta") else None, **kw)
+        assert torch.equal(got, z[name]), name
+        assert [info[k] for k in ("steps", "nfe", "n_accept", "n_reject")] == [int(v) for v in z[name + "_info"]], name
