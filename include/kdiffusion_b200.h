@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define KDB_ABI_VERSION 5
+#define KDB_ABI_VERSION 6
 
 #define KDB_ERR_BAD_ARG      (-1)
 #define KDB_ERR_UNSUPPORTED  (-2)
@@ -84,6 +84,13 @@ int kdb_solver_lincomb(const float* const* in_host, const float* coef_host, int 
 /* out = uncond + (cond - uncond) * scale: classifier-free guidance combine of the two halves of a doubled batch
  * (train.py:333-344 make_cfg_model_fn), same operation order as the reference. */
 int kdb_solver_cfg_combine(const float* uncond, const float* cond, float* out, int64_t n, float scale, void* stream);
+
+/* partials[0] = sum_i ((x_low[i] - x_high[i]) / max(atol, rtol * max(|x_low[i]|, |x_prev[i]|)))^2 : the local error estimate of
+ * the adaptive DPM-Solver (sampling.py:466-468; the caller takes sqrt(. / n)).  partials: device scratch of >= 512 floats;
+ * deterministic (fixed grid, partial sums added in index order). */
+#define KDB_DPM_ERROR_SCRATCH 512
+int kdb_solver_dpm_error(const float* x_low, const float* x_high, const float* x_prev, int64_t n, float atol, float rtol,
+                         float* partials, void* stream);
 
 /* out[b,...] = (x[b,...] - den[b,...]) / sigma[b]      (sampling.py:46-48 to_d; sigma is [B]) */
 int kdb_solver_to_d(const float* x, const float* den, const float* sigma, float* out,

@@ -346,6 +346,41 @@ __global__ void __launch_bounds__(256) noise_brownian_kernel(float* __restrict__
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// error norm of the adaptive DPM-Solver (sampling.py:466-468): sum over the latent of ((lo - hi) / max(atol, rtol max(|lo|, |prev|)))^2.
+// Deterministic two-stage reduction: each CTA writes one partial (fixed grid, fixed order inside the CTA), the last stage adds the
+// partials in index order.  partials[0] = result, partials[1 + b] = CTA b.
+// ------------------------------------------------------------------------------------------------
+constexpr int kErrBlocks = 296, kErrThreads = 256;
+
+__global__ void __launch_bounds__(kErrThreads) dpm_error_partial_kernel(const float* __restrict__ lo, const float* __restrict__ hi,
+                                                                        const float* __restrict__ prev, int64_t n, float atol, float rtol,
+                                                                        float* __restrict__ partials) {
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * kErrThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kErrThreads) {
+    const float a = __ldg(lo + i), b = __ldg(hi + i), c = __ldg(prev + i);
+    const float delta = fmaxf(atol, rtol * fmaxf(fabsf(a), fabsf(c)));
+    const float v = (a - b) / delta;
+    acc = fmaf(v, v, acc);
+  }
+  __shared__ float red[kErrThreads];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = kErrThreads / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partials[1 + blockIdx.x] = red[0];
+}
+
+__global__ void __launch_bounds__(32) dpm_error_final_kernel(float* __restrict__ partials, int blocks) {
+  if (threadIdx.x == 0) {
+    double acc = 0.0;
+    for (int b = 0; b < blocks; ++b) acc += (double)partials[1 + b];
+    partials[0] = (float)acc;
+  }
+}
+
 }  // namespace kdb
 
 using namespace kdb;
@@ -425,6 +460,16 @@ int kdb_solver_cfg_combine(const float* uncond, const float* cond, float* out, i
   EwParams p{};
   p.in[0] = uncond; p.in[1] = cond; p.out = out; p.c[0] = scale; p.n = n;
   return ew_launch<OP_CFG>(p, 2, (cudaStream_t)stream);
+}
+
+int kdb_solver_dpm_error(const float* x_low, const float* x_high, const float* x_prev, int64_t n, float atol, float rtol, float* partials,
+                         void* stream) {
+  KDB_REQUIRE(x_low && x_high && x_prev && partials && n > 0, KDB_ERR_BAD_ARG, "dpm_error: bad args");
+  dpm_error_partial_kernel<<<kErrBlocks, kErrThreads, 0, (cudaStream_t)stream>>>(x_low, x_high, x_prev, n, atol, rtol, partials);
+  KDB_LAUNCH_CHECK(F_SOLVER, (cudaStream_t)stream);
+  dpm_error_final_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(partials, kErrBlocks);
+  KDB_LAUNCH_CHECK(F_SOLVER, (cudaStream_t)stream);
+  return 0;
 }
 
 int kdb_solver_heun_correct(const float* x, const float* den1, const float* x2, const float* den2, float* x_out, int64_t n,

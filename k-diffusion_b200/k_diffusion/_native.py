@@ -5,6 +5,7 @@ device the call raises.  PyTorch is used only for device memory, streams and vie
 """
 import contextlib
 import ctypes
+import math
 import functools
 import os
 from pathlib import Path
@@ -17,7 +18,7 @@ LIB_PATH = Path(os.environ.get("KDB200_LIB", _HERE / "_lib" / "libkdb200.so"))
 PREC_FP32, PREC_BF16 = 0, 1
 ATTN_NONE, ATTN_GLOBAL, ATTN_NEIGHBORHOOD, ATTN_SHIFTED_WINDOW = 0, 1, 2, 3
 MAX_LEVELS = 8
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 _vp, _i32, _i64, _f32, _f64, _u64, _sz = (ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double,
                                            ctypes.c_uint64, ctypes.c_size_t)
@@ -46,6 +47,7 @@ SIGNATURES = {
     "kdb_solver_dpmpp_2m_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _vp]),
     "kdb_solver_lincomb": (_i32, [ctypes.POINTER(_vp), ctypes.POINTER(_f32), _i32, _vp, _i64, _vp]),
     "kdb_solver_cfg_combine": (_i32, [_vp, _vp, _vp, _i64, _f32, _vp]),
+    "kdb_solver_dpm_error": (_i32, [_vp, _vp, _vp, _i64, _f32, _f32, _vp, _vp]),
     "kdb_solver_to_d": (_i32, [_vp, _vp, _vp, _vp, _i32, _i64, _vp]),
     "kdb_precond_scale_in": (_i32, [_vp, _vp, _f32, _vp, _i32, _i64, _vp]),
     "kdb_precond_combine": (_i32, [_vp, _vp, _vp, _f32, _vp, _i32, _i64, _vp]),
@@ -241,6 +243,16 @@ def cfg_combine(uncond, cond, scale, out=None):
     out = _out_like(uncond, out)
     check(lib().kdb_solver_cfg_combine(ptr(uncond), ptr(cond), ptr(out), uncond.numel(), float(scale), stream()))
     return out
+
+
+@_on_device_of_first
+def dpm_error(x_low, x_high, x_prev, atol, rtol):
+    """||(x_low - x_high) / max(atol, rtol * max(|x_low|, |x_prev|))||_2 / sqrt(numel) as a Python float (one device->host read: the adaptive
+    DPM-Solver decides accept / reject on the host, sampling.py:466-470 of the reference)."""
+    require_cuda(x_low, x_high, x_prev)
+    scratch = torch.empty(512, dtype=torch.float32, device=x_low.device)
+    check(lib().kdb_solver_dpm_error(ptr(f32c(x_low)), ptr(f32c(x_high)), ptr(f32c(x_prev)), x_low.numel(), float(atol), float(rtol), ptr(scratch), stream()))
+    return math.sqrt(float(scratch[0])) / math.sqrt(x_low.numel())
 
 
 @_on_device_of_first

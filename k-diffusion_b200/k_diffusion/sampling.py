@@ -2,7 +2,8 @@
 
 Drop-in for the functions of reference `k_diffusion/sampling.py` that are on the north-star path:
 schedules (:17-43), `to_d` (:46), `get_ancestral_step` (:51), noise samplers (:61-114),
-`sample_euler` (:117), `sample_euler_ancestral` (:138), `sample_heun` (:158), `sample_dpmpp_2m` (:584).
+`sample_euler` (:117), `sample_euler_ancestral` (:138), `sample_heun` (:158), `sample_dpmpp_2m` (:584), and of the callers around it:
+the other fixed-schedule samplers (:186-278, :519-700), DPM-Solver fast / adaptive (:303-516), the CFG wrapper of train.py:333-344.
 
 How this differs from the reference implementation:
   * the sigma schedule is pulled to the host ONCE; every per-step coefficient is a host scalar, so
@@ -802,9 +803,11 @@ def sample_dpmpp_2m(model, x, sigmas, extra_args=None, callback=None, disable=No
 # against reference trajectories (tests/test_host_logic.py).  GPU parity tests for these entry points land with round 2.
 # --------------------------------------------------------------------------------------------
 
-def _sample_ops(name, model, x, sigmas, plan_fn, extra_args, callback, disable, params, noise_sampler=None, churn_noise=0.):
+def _sample_ops(name, model, x, sigmas, plan_fn, extra_args, callback, disable, params, noise_sampler=None, churn_noise=0., callback_extra=None):
+    """Run a generic op plan.  `plan_fn(sig)` builds it from the host copy of `sigmas` (or is the plan itself, a list);
+    `callback_extra(st)` may add keys to the callback payload of a step."""
     xw, sig, extra_args = _prepare(x, sigmas, extra_args)
-    plan = plan_fn(sig)
+    plan = plan_fn if isinstance(plan_fn, list) else plan_fn(sig)
     needs_noise = any(op[0] == 'noise' for st in plan for op in st['ops'])
     ours = isinstance(noise_sampler, (BrownianTreeNoiseSampler, PhiloxNoiseSampler))
     churned = any(st.get('gamma', 0) > 0 for st in plan)
@@ -824,7 +827,7 @@ def _sample_ops(name, model, x, sigmas, plan_fn, extra_args, callback, disable, 
                     k += 1
                     if first and callback is not None:
                         callback({'x': T[op[2]], 'i': st['i'], 'sigma': sigmas[st['i']], 'sigma_hat': _scalar_like(sigmas, st['sigma_hat']),
-                                  'denoised': T[op[1]]})
+                                  'denoised': T[op[1]], **({} if callback_extra is None else callback_extra(st))})
                     first = False
                 elif kind == 'lin':
                     T[op[1]] = _native.lincomb([T[n] for n, _ in op[2]], [float(c) for _, c in op[2]])
@@ -906,3 +909,192 @@ def sample_dpmpp_3m_sde(model, x, sigmas, extra_args=None, callback=None, disabl
     noise_sampler = _default_brownian(x, sigmas) if noise_sampler is None else noise_sampler
     return _sample_ops('dpmpp_3m_sde', model, x, sigmas, lambda sig: plan_dpmpp_3m_sde(sig, eta, s_noise), extra_args, callback, disable,
                        (eta, s_noise), noise_sampler)
+
+
+# --------------------------------------------------------------------------------------------
+# DPM-Solver: fixed-step "fast" and adaptive 12 / 23 (reference sampling.py:303-516)
+# --------------------------------------------------------------------------------------------
+
+class PIDStepSizeController:
+    """A PID controller for ODE adaptive step size control (reference sampling.py:303-330; pure host arithmetic)."""
+
+    def __init__(self, h, pcoeff, icoeff, dcoeff, order=1, accept_safety=0.81, eps=1e-8):
+        self.h = h
+        self.b1 = (pcoeff + icoeff + dcoeff) / order
+        self.b2 = -(pcoeff + 2 * dcoeff) / order
+        self.b3 = dcoeff / order
+        self.accept_safety = accept_safety
+        self.eps = eps
+        self.errs = []
+
+    def limiter(self, x):
+        return 1 + math.atan(x - 1)
+
+    def propose_step(self, error):
+        inv_error = 1 / (float(error) + self.eps)
+        if not self.errs:
+            self.errs = [inv_error, inv_error, inv_error]
+        self.errs[0] = inv_error
+        factor = self.errs[0] ** self.b1 * self.errs[1] ** self.b2 * self.errs[2] ** self.b3
+        factor = self.limiter(factor)
+        accept = factor >= self.accept_safety
+        if accept:
+            self.errs[2] = self.errs[1]
+            self.errs[1] = self.errs[0]
+        self.h *= factor
+        return accept
+
+
+def _dpm_t(sigma):
+    """t = -log(sigma) as the reference computes it: an fp32 tensor op (DPMSolver.t, sampling.py:343-344)."""
+    return float(-torch.tensor(float(sigma)).log())
+
+
+def _dpm_sigma(t):
+    return math.exp(-t)
+
+
+def _dpm_eps_op(dst, x_name, den_name, sigma):
+    """eps = (x - den) / sigma as one lincomb (DPMSolver.eps, sampling.py:350-357)"""
+    return ('lin', dst, [(x_name, 1 / sigma), (den_name, -1 / sigma)])
+
+
+def _dpm_step_ops(t, t_next, order, dst, r1=None):
+    """DPM-Solver step of order 1 / 2 / 3 from t to t_next (sampling.py:359-388) as lincombs over x, eps = (x - D(x, sigma(t))) / sigma(t)
+    (already in 'eps') and the intermediate states -- the reference's own association: combining x with u1 / u2 directly would
+    cancel ~13 |x| at sigma 80 and lose three digits.
+      order 1:  x - A eps
+      order 2:  u1 = x - B eps;  x - (A - C) eps - C eps_r1
+      order 3:  u1 = x - B1 eps;  u2 = x - (B2 - D2) eps - D2 eps_r1;  x - (A - E) eps - E eps_r2
+    Returns (ops, sigmas of the EXTRA evaluations)."""
+    h = t_next - t
+    sn = _dpm_sigma(t_next)
+    A = sn * math.expm1(h)
+    if order == 1:
+        return [('lin', dst, [('x', 1.), ('eps', -A)])], []
+    if order == 2:
+        r1 = 1 / 2 if r1 is None else r1
+        s1s = _dpm_sigma(t + r1 * h)
+        B = s1s * math.expm1(r1 * h)
+        C = sn / (2 * r1) * math.expm1(h)
+        return [('lin', 'u1', [('x', 1.), ('eps', -B)]), ('eval', 'den1', 'u1'), _dpm_eps_op('eps1', 'u1', 'den1', s1s),
+                ('lin', dst, [('x', 1.), ('eps', -(A - C)), ('eps1', -C)])], [s1s]
+    r1, r2 = 1 / 3, 2 / 3
+    s1s, s2s = _dpm_sigma(t + r1 * h), _dpm_sigma(t + r2 * h)
+    B1 = s1s * math.expm1(r1 * h)
+    B2 = s2s * math.expm1(r2 * h)
+    D2 = s2s * (r2 / r1) * (math.expm1(r2 * h) / (r2 * h) - 1)
+    E = sn / r2 * (math.expm1(h) / h - 1)
+    return [('lin', 'u1', [('x', 1.), ('eps', -B1)]), ('eval', 'den1', 'u1'), _dpm_eps_op('eps1', 'u1', 'den1', s1s),
+            ('lin', 'u2', [('x', 1.), ('eps', -(B2 - D2)), ('eps1', -D2)]), ('eval', 'den2', 'u2'), _dpm_eps_op('eps2', 'u2', 'den2', s2s),
+            ('lin', dst, [('x', 1.), ('eps', -(A - E)), ('eps2', -E)])], [s1s, s2s]
+
+
+def _dpm_ancestral_target(t, t_next, t_end, eta):
+    """(t_next_, su) of the stochastic variants (sampling.py:421-426, :455-460).  sigma_down comes from a cancelling difference of
+    squares: it is evaluated with the reference's own fp32 tensor ops (host-side 0-dim tensors) so the shortened step matches bit for bit."""
+    if not eta:
+        return t_next, 0.
+    T = lambda v: torch.tensor(float(v), dtype=torch.float32)
+    sig = lambda u: u.neg().exp()
+    sd, _ = get_ancestral_step(sig(T(t)), sig(T(t_next)), eta)
+    t_down = torch.minimum(T(t_end), -sd.log())
+    su = (sig(T(t_next)) ** 2 - sig(t_down) ** 2) ** 0.5
+    return float(t_down), float(su)
+
+
+def plan_dpm_fast(sigma_min, sigma_max, n, eta=0., s_noise=1.):
+    """Host plan of dpm_solver_fast (sampling.py:403-433): (plan, ts) with ts the fp32 time grid as Python floats."""
+    if sigma_min <= 0 or sigma_max <= 0:
+        raise ValueError('sigma_min and sigma_max must not be 0')
+    m = math.floor(n / 3) + 1
+    ts = [float(v) for v in torch.linspace(-torch.tensor(float(sigma_max)).log(), -torch.tensor(float(sigma_min)).log(), m + 1)]
+    orders = [3] * (m - 2) + [2, 1] if n % 3 == 0 else [3] * (m - 1) + [n % 3]
+    plan = []
+    for i, order in enumerate(orders):
+        t, t_next = ts[i], ts[i + 1]
+        t_down, su = _dpm_ancestral_target(t, t_next, ts[-1], eta)
+        ops, extra = _dpm_step_ops(t, t_down, order, 'x')
+        ops = [('eval', 'den', 'x'), _dpm_eps_op('eps', 'x', 'den', _dpm_sigma(t))] + ops
+        if eta:
+            ops += [('noise', 'n', _dpm_sigma(t), _dpm_sigma(t_next)), ('lin', 'x', [('x', 1.), ('n', su * s_noise)])]
+        plan.append(dict(i=i, sigma_hat=_dpm_sigma(t), t=t, ops=ops, evals=[_dpm_sigma(t)] + extra))
+    return plan, ts
+
+
+@_on_x_device
+@torch.no_grad()
+def sample_dpm_fast(model, x, sigma_min, sigma_max, n, extra_args=None, callback=None, disable=None, eta=0., s_noise=1., noise_sampler=None):
+    """DPM-Solver-Fast (fixed step size). See https://arxiv.org/abs/2206.00927.  (reference sampling.py:491-501)
+    With eta = 0 no noise is drawn at all (the reference draws and multiplies by 0: same samples, different global RNG offset)."""
+    plan, ts = plan_dpm_fast(sigma_min, sigma_max, n, eta, s_noise)
+    sigmas = torch.tensor([_dpm_sigma(t) for t in ts], dtype=torch.float32, device=x.device)
+    if eta and noise_sampler is None:
+        noise_sampler = default_noise_sampler(_native.f32c(x))
+    extra = lambda st: {'t': _scalar_like(sigmas, st['t']), 't_up': _scalar_like(sigmas, st['t'])}
+    return _sample_ops('dpm_fast', model, x, sigmas, plan, extra_args, callback, disable, (float(sigma_min), float(sigma_max), n, eta, s_noise),
+                       noise_sampler if eta else None, callback_extra=extra)
+
+
+@_on_x_device
+@torch.no_grad()
+def sample_dpm_adaptive(model, x, sigma_min, sigma_max, extra_args=None, callback=None, disable=None, order=3, rtol=0.05, atol=0.0078, h_init=0.05,
+                        pcoeff=0., icoeff=1., dcoeff=0., accept_safety=0.81, eta=0., s_noise=1., noise_sampler=None, return_info=False):
+    """DPM-Solver-12 and 23 (adaptive step size). See https://arxiv.org/abs/2206.00927.  (reference sampling.py:435-488, :504-516)
+    The step size depends on the data: every step reads one error norm back to the host (`kdb_solver_dpm_error`), so this sampler is
+    not captured into a CUDA graph.  Model evaluations, state updates and the error reduction are libkdb200 kernels."""
+    if sigma_min <= 0 or sigma_max <= 0:
+        raise ValueError('sigma_min and sigma_max must not be 0')
+    if order not in {2, 3}:
+        raise ValueError('order should be 2 or 3')
+    _native.require_cuda(x)
+    extra_args = {} if extra_args is None else extra_args
+    xc = _native.f32c(x)
+    ours = isinstance(noise_sampler, (BrownianTreeNoiseSampler, PhiloxNoiseSampler))
+    if eta and noise_sampler is None:
+        noise_sampler, ours = default_noise_sampler(xc), True
+    t_start, t_end = f32(_dpm_t(sigma_max)), f32(_dpm_t(sigma_min))
+    pid = PIDStepSizeController(abs(h_init), pcoeff, icoeff, dcoeff, 1.5 if eta else order, accept_safety)
+    s, x_prev = t_start, xc
+    info = {'steps': 0, 'nfe': 0, 'n_accept': 0, 'n_reject': 0}
+    while s < f32(t_end - f32(1e-5)):                     # (the reference's s and t are fp32 tensors: same roundings here)
+        t = min(t_end, f32(s + f32(pid.h)))
+        t_down, su = _dpm_ancestral_target(float(s), float(t), float(t_end), eta)
+        if order == 2:
+            lo_ops, _ = _dpm_step_ops(float(s), t_down, 1, 'lo')
+            hi_ops, evals = _dpm_step_ops(float(s), t_down, 2, 'hi')
+            ops = lo_ops + hi_ops
+        else:                                              # the order-2 estimate reuses the order-3 step's first stage (same eps_r1 cache key)
+            hi_ops, evals = _dpm_step_ops(float(s), t_down, 3, 'hi')
+            lo_ops, _ = _dpm_step_ops(float(s), t_down, 2, 'lo', r1=1 / 3)
+            ops = hi_ops[:3] + [lo_ops[3]] + hi_ops[3:]      # u1, den1, eps1 | lo | u2, den2, eps2, hi
+        ev = _Evaluator(model, xc, extra_args, [_dpm_sigma(float(s))] + evals)
+        T = {'x': xc, 'den': ev(0, xc)}
+        ops = [_dpm_eps_op('eps', 'x', 'den', _dpm_sigma(float(s)))] + ops
+        k = 1
+        for op in ops:
+            if op[0] == 'eval':
+                T[op[1]] = ev(k, T[op[2]])
+                k += 1
+            else:
+                T[op[1]] = _native.lincomb([T[n_] for n_, _ in op[2]], [float(c) for _, c in op[2]])
+        error = _native.dpm_error(T['lo'], T['hi'], x_prev, atol, rtol)
+        accept = pid.propose_step(error)
+        if accept:
+            x_prev = T['lo']
+            xc = T['hi']
+            if eta:
+                args = (_dpm_sigma(float(s)), _dpm_sigma(float(t))) if ours else (_scalar_like(xc, _dpm_sigma(float(s))), _scalar_like(xc, _dpm_sigma(float(t))))
+                xc = _native.lincomb([xc, _native.f32c(noise_sampler(*args))], [1., su * s_noise])
+            s = t
+            info['n_accept'] += 1
+        else:
+            info['n_reject'] += 1
+        info['nfe'] += order
+        info['steps'] += 1
+        if callback is not None:
+            sg = _scalar_like(xc, _dpm_sigma(float(s)))
+            callback({'sigma': sg, 'sigma_hat': sg, 'x': xc, 'i': info['steps'] - 1, 't': _scalar_like(xc, float(s)), 't_up': _scalar_like(xc, float(s)),
+                      'denoised': T['den'], 'error': error, 'h': pid.h, **info})
+    out = _finish(xc, x)
+    return (out, info) if return_info else out

@@ -184,3 +184,75 @@ def test_cfg_wrapper_vs_oracle(monkeypatch):
     xin, uncond = x, torch.full_like(cc2, 10)
     ref = toy(xin, sig.to(DEV), uncond) + (toy(xin, sig.to(DEV), cc2) - toy(xin, sig.to(DEV), uncond)) * 2.0
     assert_close(tfn(xin, sig.to(DEV), class_cond=cc2), ref, rtol=1e-5, atol=1e-6, what="cfg around an opaque model")
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# DPM-Solver fast / adaptive (reference sampling.py:303-516; goldens from oracle/make_golden_dpm.py)
+# ------------------------------------------------------------------------------------------------------------------------------
+DPM_ADAPTIVE = {"dpm_adaptive_o3": dict(), "dpm_adaptive_o2": dict(order=2), "dpm_adaptive_o3_tight": dict(rtol=0.01, atol=0.002, h_init=0.1),
+                "dpm_adaptive_o3_pid": dict(pcoeff=0.2, icoeff=0.7, dcoeff=0.1, accept_safety=0.9), "dpm_adaptive_o3_eta05": dict(eta=0.5, s_noise=0.9)}
+
+
+def _scale_close(got, want, what, rel=1e-3):
+    """North-star rtol against the signal's scale: the sigma-80 toy problem amplifies a 1e-7 coefficient change to ~2e-4 (see the
+    comment in tests/test_host_logic.py::test_dpm_solver_plans_and_entry_points_with_stubbed_kernels)."""
+    err = float((got.detach().float().cpu() - want).abs().max())
+    assert err <= rel * float(want.abs().max()), f"{what}: max abs err {err:.3e} vs scale {float(want.abs().max()):.3e}"
+
+
+@pytest.mark.parametrize("n", [4, 5, 6, 9, 10])
+def test_dpm_fast_opaque_model_vs_reference(n):
+    z = load_npz("toy_dpm_solvers.npz")
+    _scale_close(S.sample_dpm_fast(toy2, z["x"].to(DEV), 1e-2, 80., n, disable=True), z[f"dpm_fast_n{n}"], f"dpm_fast n={n}", rel=2e-4)
+
+
+def test_dpm_fast_stochastic_opaque_model_vs_reference():
+    z = load_npz("toy_dpm_solvers.npz")
+    x, nz = z["x"].to(DEV), z["noise"].to(DEV)
+    it = iter(nz)
+    got = S.sample_dpm_fast(toy2, x, 1e-2, 80., 7, disable=True, eta=0.5, s_noise=0.9, noise_sampler=lambda a, b: next(it))
+    _scale_close(got, z["dpm_fast_n7_eta05"], "dpm_fast n=7 eta=0.5", rel=2e-4)
+    it = iter(nz)
+    _scale_close(S.sample_dpm_fast(toy2, x, 1e-2, 80., 6, disable=True, eta=1.0, noise_sampler=lambda a, b: next(it)), z["dpm_fast_n6_eta1"], "dpm_fast n=6 eta=1")
+
+
+@pytest.mark.parametrize("name", sorted(DPM_ADAPTIVE))
+def test_dpm_adaptive_opaque_model_vs_reference(name):
+    """Same accept / reject sequence as the reference (the error norm is kdb_solver_dpm_error) and the same samples."""
+    z = load_npz("toy_dpm_solvers.npz")
+    kw = dict(DPM_ADAPTIVE[name])
+    if kw.get("eta"):
+        it = iter(z["noise"].to(DEV))
+        kw["noise_sampler"] = lambda a, b: next(it)
+    got, info = S.sample_dpm_adaptive(toy2, z["x"].to(DEV), 1e-2, 80., disable=True, return_info=True, **kw)
+    assert [info[k] for k in ("steps", "nfe", "n_accept", "n_reject")] == [int(v) for v in z[name + "_info"]], (name, info)
+    _scale_close(got, z[name], name)
+
+
+def test_dpm_error_kernel_matches_torch():
+    from k_diffusion import _native
+    g = torch.Generator(device=DEV).manual_seed(5)
+    lo = torch.randn(4, 3, 64, 64, device=DEV, generator=g) * 3
+    hi = lo + torch.randn(4, 3, 64, 64, device=DEV, generator=g) * 0.05
+    prev = torch.randn(4, 3, 64, 64, device=DEV, generator=g) * 3
+    delta = torch.maximum(torch.tensor(0.0078, device=DEV), 0.05 * torch.maximum(lo.abs(), prev.abs()))
+    want = float(torch.linalg.norm(((lo - hi) / delta).double()) / lo.numel() ** 0.5)
+    got = _native.dpm_error(lo, hi, prev, 0.0078, 0.05)
+    assert abs(got - want) <= 1e-5 * want
+    assert _native.dpm_error(lo, hi, prev, 0.0078, 0.05) == got          # deterministic reduction
+
+
+def test_dpm_solvers_native_model_vs_oracle():
+    """cfg1 (MNIST transformer, class-conditional, fp32 exact path): the native engine behind sample_dpm_fast (graph-captured op plan)
+    and sample_dpm_adaptive (eager host loop) against the CPU oracle on the same inputs."""
+    cfg, sd, inner, model, z = build("cfg1_mnist")
+    x = z["x"].to(DEV)
+    cc = z["class_cond"]
+    ea = dict(class_cond=cc.to(DEV))
+    oracle_model = O.make_denoiser(sd, cfg["model"])
+    om = lambda xx, ss, **kw: oracle_model(xx, ss, class_cond=cc)
+    _scale_close(S.sample_dpm_fast(model, x, 1e-2, 80., 7, extra_args=ea, disable=True), O.sample_dpm_fast(om, z["x"], 1e-2, 80., 7), "native dpm_fast")
+    got, info = S.sample_dpm_adaptive(model, x, 1e-2, 80., extra_args=ea, disable=True, return_info=True)
+    want, winfo = O.sample_dpm_adaptive(om, z["x"], 1e-2, 80.)
+    assert info == winfo, (info, winfo)
+    _scale_close(got, want, "native dpm_adaptive", rel=2e-3)

@@ -275,3 +275,56 @@ def test_attention_pipeline_barrier_protocol_model():
         for n_local in (0, 1, 2, 3, 7):
             for seed in range(25):
                 assert sim.run(n_local, nb, shared, seed)
+
+
+def test_dpm_solver_plans_and_entry_points_with_stubbed_kernels(monkeypatch):
+    """sample_dpm_fast (an op plan like the other fixed-schedule samplers) and sample_dpm_adaptive (host PID loop
+    around the same lincomb / evaluation / error-norm primitives) against outputs recorded from the reference
+    (oracle/make_golden_dpm.py), step and rejection counts included.  Native primitives replaced by torch one-liners (test-only)."""
+    from k_diffusion import _native
+    monkeypatch.setattr(_native, "require_cuda", lambda *t: None)
+    monkeypatch.setattr(_native, "f32c", lambda t: t.to(torch.float32).contiguous())
+    monkeypatch.setattr(_native, "lincomb", lambda ts, cs, out=None: sum(np.float32(c) * t for t, c in zip(ts, cs)))
+
+    def dpm_error(lo, hi, prev, atol, rtol):
+        delta = torch.maximum(torch.tensor(atol), torch.tensor(rtol) * torch.maximum(lo.abs(), prev.abs()))
+        return float(torch.linalg.norm((lo - hi) / delta) / lo.numel() ** 0.5)
+
+    monkeypatch.setattr(_native, "dpm_error", dpm_error)
+    monkeypatch.setattr(S, "_on_x_device", lambda fn: fn, raising=False)
+    z = load_npz("toy_dpm_solvers.npz")
+    toy2 = lambda x, s, **kw: x / (1 + s[:, None, None, None] ** 2) + 0.1 * torch.tanh(x)
+    x = z["x"]
+
+    def ns():
+        it = iter(z["noise"])
+        return lambda a, b: next(it)
+
+    fast = S.sample_dpm_fast.__wrapped__ if hasattr(S.sample_dpm_fast, "__wrapped__") else S.sample_dpm_fast
+    adaptive = S.sample_dpm_adaptive.__wrapped__ if hasattr(S.sample_dpm_adaptive, "__wrapped__") else S.sample_dpm_adaptive
+    for n in (4, 5, 6, 9, 10):
+        plan, ts = S.plan_dpm_fast(1e-2, 80., n)
+        assert sum(len(st["evals"]) for st in plan) == n                       # the NFE budget is met exactly (sampling.py:409-417)
+        assert all(len(op[2]) <= 6 for st in plan for op in st["ops"] if op[0] == "lin")
+        assert_close(fast(toy2, x, 1e-2, 80., n, disable=True), z[f"dpm_fast_n{n}"], rtol=1e-4, atol=2e-5, what=f"dpm_fast n={n}")
+    assert_close(fast(toy2, x, 1e-2, 80., 7, disable=True, eta=0.5, s_noise=0.9, noise_sampler=ns()), z["dpm_fast_n7_eta05"], rtol=1e-4, atol=2e-5)
+    # eta = 1 from sigma 80 (|x| up to 250, step coefficients ~20) is ill-conditioned in fp32: a 1e-7 relative change of any step
+    # coefficient moves the result by 2e-4, and the reference's own fp32 run sits 3.6e-4 from the float64 evaluation of the same formulas
+    # (the plan: 5.0e-4; in float64 with float64 coefficients plan and reference formulas agree to 1e-12).  North-star rtol with an
+    # absolute floor at that noise:
+    assert_close(fast(toy2, x, 1e-2, 80., 6, disable=True, eta=1.0, noise_sampler=ns()), z["dpm_fast_n6_eta1"], rtol=1e-3, atol=1e-3)
+    cases = {"dpm_adaptive_o3": dict(), "dpm_adaptive_o2": dict(order=2), "dpm_adaptive_o3_tight": dict(rtol=0.01, atol=0.002, h_init=0.1),
+             "dpm_adaptive_o3_pid": dict(pcoeff=0.2, icoeff=0.7, dcoeff=0.1, accept_safety=0.9), "dpm_adaptive_o3_eta05": dict(eta=0.5, s_noise=0.9)}
+    for name, kw in cases.items():
+        got, info = adaptive(toy2, x, 1e-2, 80., disable=True, return_info=True, noise_sampler=ns() if kw.get("eta") else None, **kw)
+        assert [info[k] for k in ("steps", "nfe", "n_accept", "n_reject")] == [int(v) for v in z[name + "_info"]], name
+        # the step sizes feed back through the error norm: coefficient differences of 1e-7 grow like in the eta = 1 case above;
+        # same accept / reject sequence, result within the north-star rtol of the signal's scale
+        assert float((got - z[name]).abs().max()) <= 1e-3 * float(z[name].abs().max()), (name, float((got - z[name]).abs().max()))
+    seen = []
+    fast(toy2, x, 1e-2, 80., 6, disable=True, callback=seen.append)
+    assert [c["i"] for c in seen] == [0, 1, 2] and {"x", "i", "sigma", "sigma_hat", "denoised", "t", "t_up"} <= set(seen[0])
+    with pytest.raises(ValueError):
+        adaptive(toy2, x, 1e-2, 80., order=4)
+    with pytest.raises(ValueError):
+        fast(toy2, x, 0., 80., 6)
