@@ -15,12 +15,12 @@
 //     Q K^T, 8 x 32 for P V) but 16384 exponentials = 1024 cycles of the SM's 16-lane MUFU unit.  So the kernel is built to keep
 //     the exponential pipe (and, for the windowed modes, the TMA queue) busy all the time and to hide everything else behind it.
 //
-// One CTA per SM, 352 threads, loops over PAIRS of 128-row query tiles:
+// One CTA per SM, 320 threads, loops over PAIRS of 128-row query tiles:
 //   warps 0-3   softmax group 0: tile 0 of the pair, thread = query row (TMEM lane), S0 / O0
 //   warps 4-7   softmax group 1: tile 1 of the pair, S1 / O1
 //   warp  8     TMA producer: the pair's Q tiles (double buffered across pairs) and a 3-stage K/V ring that runs ahead across pairs
-//   warps 9-10  tcgen05.mma issuers, one per tile of the pair (see the role's comment)
-// Per key block j issuer t runs:  wait P_t(j) -> O_t += P_t V -> S_t = Q_t K(j+1)^T, so while group t exponentiates
+//   warp  9     tcgen05.mma issuer
+// Per key block j the issuer runs, for t = 0, 1:  wait P_t(j) -> O_t += P_t V -> S_t = Q_t K(j+1)^T, so while group t exponentiates
 // block j the tensor core finishes the other group's block and the next S tile is ready the moment a group asks for it.
 //   GLOBAL : pair = 256 queries of one (image, head); both tiles share each K/V stage; nb = S / 128 key blocks
 //   NA     : tile = 8 x 16 query block of one head; its own K/V = clamped 14 x 22 halo in 3 blocks of 5 halo rows (110 keys);
@@ -107,7 +107,7 @@ __device__ __forceinline__ PipeTile pipe_decode(const PipeAttnParams& p, int pai
 }
 
 template <int MODE, bool PT>
-__global__ void __launch_bounds__(352, 1) attn_pipe_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_kv,
+__global__ void __launch_bounds__(320, 1) attn_pipe_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_kv,
                                                            const PipeAttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   constexpr bool SHARED_KV = MODE == MODE_GLOBAL;
@@ -128,14 +128,14 @@ __global__ void __launch_bounds__(352, 1) attn_pipe_kernel(const __grid_constant
     if constexpr (MODE == MODE_NA) tc::tma_prefetch_desc(&tmap_kv);
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&bars->q_full[i], 1);
-      tc::mbar_init(&bars->q_empty[i], 2);                    // one commit per MMA issuer
+      tc::mbar_init(&bars->q_empty[i], 1);
       tc::mbar_init(&bars->s_ready[i], 1);
       tc::mbar_init(&bars->p_ready[i], 128);
       tc::mbar_init(&bars->pv_done[i], 1);
     }
     for (int i = 0; i < PA_STAGES; ++i) {
       tc::mbar_init(&bars->kv_full[i], 1);
-      tc::mbar_init(&bars->kv_empty[i], SHARED_KV ? 2 : 1);    // a shared K/V stage is released by both issuers
+      tc::mbar_init(&bars->kv_empty[i], 1);
     }
     tc::fence_barrier_init();
   }
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(352, 1) attn_pipe_kernel(const __grid_constant
           }
       };
       auto kv_stage = [&](const PipeTile& x, int j) {
-        tc::mbar_wait_role(&bars->kv_empty[st], ph ^ 1u);
+        tc::mbar_wait(&bars->kv_empty[st], ph ^ 1u);
         tc::mbar_arrive_expect_tx(&bars->kv_full[st], 2 * KV_BYTES);
         PA_TRACE(0, 100 + j);
         uint8_t* k = sKV + (size_t)(st * 2) * TILE_BYTES;
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(352, 1) attn_pipe_kernel(const __grid_constant
         const int pair = (int)blockIdx.x + u * (int)gridDim.x;
         const PipeTile x0 = pipe_decode<MODE>(p, pair, 0), x1 = pipe_decode<MODE>(p, pair, 1);
         const int qb = u & 1;
-        tc::mbar_wait_role(&bars->q_empty[qb], (uint32_t)(((u >> 1) & 1) ^ 1));
+        tc::mbar_wait(&bars->q_empty[qb], (uint32_t)(((u >> 1) & 1) ^ 1));
         tc::mbar_arrive_expect_tx(&bars->q_full[qb], 2 * TILE_BYTES);
         PA_TRACE(0, 1);
 #pragma unroll
@@ -229,81 +229,92 @@ __global__ void __launch_bounds__(352, 1) attn_pipe_kernel(const __grid_constant
         }
       }
     }
-  } else if (warp >= 9) {
-    // ------------------------------------------------------------------ MMA issuers
-    // One issuing thread PER TILE of the pair (warps 9 and 10).  The tensor pipe queues almost nothing behind the executing
-    // tcgen05.mma (tools/mma_dual_issue_bench.cu), so every mbarrier wait and every instruction between two issues is tensor idle
-    // time; with a single issuer group 1's P V / next S also sat behind group 0's waits.  Issuer t owns the chain of softmax group t:
-    //   wait P_t(j) -> O_t += P_t V(j) -> wait K/V(j+1) -> S_t = Q_t K(j+1)^T
-    // and its MMAs interleave with the other issuer's in the pipe.  tcgen05.commit covers the committing thread's MMAs only: a K/V
-    // stage shared by both tiles (GLOBAL) and the pair's Q buffers collect one commit from each issuer (barriers expect two).
-    const int t = warp - 9;
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------ MMA issuer
     if (tc::elect_one()) {
       constexpr uint32_t IDESC_S = tc::idesc_bf16(ROWS, 128);
       constexpr uint32_t IDESC_O = tc::idesc_bf16(ROWS, DH, 0, 1);
       const uint32_t q_base = tc::smem_u32(sQ), kv_base = tc::smem_u32(sKV), p_base = tc::smem_u32(sP);
-      // ring cursor of THIS tile's next K/V stage in consumption order: the producer fills (pair, block, tile) in that order, one
-      // stage per block when the tiles share K/V, else one per (block, tile)
-      constexpr uint32_t STEP = SHARED_KV ? 1u : 2u;
-      uint32_t rs = SHARED_KV ? 0u : (uint32_t)t, rph = 0;
-      auto take = [&](uint32_t& s_, uint32_t& ph_) {
-        s_ = rs;
-        ph_ = rph;
-        rs += STEP;
-        if (rs >= (uint32_t)PA_STAGES) {
-          rs -= (uint32_t)PA_STAGES;
+      uint32_t rs = 0, rph = 0;         // ring cursor: next K/V stage in consumption order
+      uint32_t n_p[2] = {0, 0};         // P tiles consumed per group (parity of p_ready)
+      auto take = [&](uint32_t& s, uint32_t& ph) {       // hand out the cursor's stage, advance the cursor
+        s = rs;
+        ph = rph;
+        if (++rs == PA_STAGES) {
+          rs = 0;
           rph ^= 1u;
         }
       };
-      uint32_t n_p = 0;                 // P tiles consumed (parity of p_ready[t])
-      auto issue_s = [&](int qb, uint32_t stage) {
+      auto issue_s = [&](int t, int qb, uint32_t stage) {
         const uint64_t qd = tc::smem_desc_k_sw128(q_base + (uint32_t)((qb * 2 + t) * TILE_BYTES));
         const uint64_t kd = tc::smem_desc_k_sw128(kv_base + (uint32_t)((stage * 2) * TILE_BYTES));
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k) tc::umma_bf16(tmem + (uint32_t)(t * 128), qd + 2ull * k, kd + 2ull * k, IDESC_S, (uint32_t)(k != 0));
         tc::umma_commit(&bars->s_ready[t]);
-        if (t == 0) PA_TRACE(1, 10);
+        PA_TRACE(1, 10 + t);
       };
       for (int u = 0; u < n_local; ++u) {
         const int qb = u & 1;
-        uint32_t cs, cph, ns = 0, nph = 0;
-        take(cs, cph);
-        tc::mbar_wait_role(&bars->q_full[qb], (uint32_t)((u >> 1) & 1));
-        if (t == 0) PA_TRACE(1, 2);
-        // S tile of the pair's first key block.  S_t is free: p_ready of the previous pair's last block was waited below.
-        tc::mbar_wait_role(&bars->kv_full[cs], cph);
-        tc::tc_fence_after();
-        issue_s(qb, cs);
+        uint32_t cs[2], cph[2], ns[2] = {0, 0}, nph[2] = {0, 0};
+        take(cs[0], cph[0]);
+        if constexpr (SHARED_KV) {
+          cs[1] = cs[0];
+          cph[1] = cph[0];
+        } else {
+          take(cs[1], cph[1]);
+        }
+        tc::mbar_wait(&bars->q_full[qb], (uint32_t)((u >> 1) & 1));
+        PA_TRACE(1, 2);
+        // S tiles of the pair's first key block.  S_t is free: p_ready of the previous pair's last block was waited below.
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (t == 0 || !SHARED_KV) tc::mbar_wait(&bars->kv_full[cs[t]], cph[t]);
+          tc::tc_fence_after();
+          issue_s(t, qb, cs[t]);
+        }
         for (int j = 0; j < nb; ++j) {
           const bool more = j + 1 < nb;
-          if (more) take(ns, nph);
-          tc::mbar_wait_role(&bars->p_ready[t], n_p & 1u);          // P_t(j) is written, S_t(j) fully read
-          ++n_p;
-          if (t == 0) PA_TRACE(1, 20);
-          // (O_t of the previous pair has left TMEM: the group reads it before it starts the tile whose P_t was just awaited)
-          tc::tc_fence_after();
-          const uint64_t vd = tc::smem_desc_mn_sw128(kv_base + (uint32_t)((cs * 2 + 1) * TILE_BYTES), 1024, 1024);
-          if constexpr (PT) {        // A = P_t in TMEM: 8 columns (16 bf16) per k-step, over the first 64 columns of S_t
-#pragma unroll
-            for (int k = 0; k < ROWS / 16; ++k)
-              tc::umma_bf16_ts(tmem + 256u + (uint32_t)(t * 64), tmem + (uint32_t)(t * 128 + k * 8), vd + (uint64_t)(k * ((16 * 128) >> 4)), IDESC_O,
-                               (uint32_t)((j | k) != 0));
-          } else {
-            const uint64_t pd = tc::smem_desc_k_sw128(p_base + (uint32_t)(t * 2 * TILE_BYTES));
-#pragma unroll
-            for (int k = 0; k < ROWS / 16; ++k)
-              tc::umma_bf16(tmem + 256u + (uint32_t)(t * 64), pd + (uint64_t)((k >> 2) * (TILE_BYTES >> 4)) + 2ull * (k & 3),
-                            vd + (uint64_t)(k * ((16 * 128) >> 4)), IDESC_O, (uint32_t)((j | k) != 0));
+          if (more) {
+            take(ns[0], nph[0]);
+            if constexpr (SHARED_KV) {
+              ns[1] = ns[0];
+              nph[1] = nph[0];
+            } else {
+              take(ns[1], nph[1]);
+            }
           }
-          tc::umma_commit(&bars->pv_done[t]);
-          tc::umma_commit(&bars->kv_empty[cs]);                  // every MMA of THIS issuer that reads the stage has been issued
-          if (more) {                                             // next block's S tile
-            tc::mbar_wait_role(&bars->kv_full[ns], nph);
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            tc::mbar_wait(&bars->p_ready[t], n_p[t] & 1u);          // P_t(j) is in shared memory, S_t(j) fully read
+            ++n_p[t];
+            PA_TRACE(1, 20 + t);
+            // (O_t of the previous pair has left TMEM: the group reads it before it starts the tile whose P_t was just awaited)
             tc::tc_fence_after();
-            issue_s(qb, ns);
+            const uint64_t vd = tc::smem_desc_mn_sw128(kv_base + (uint32_t)((cs[t] * 2 + 1) * TILE_BYTES), 1024, 1024);
+            if constexpr (PT) {        // A = P_t in TMEM: 8 columns (16 bf16) per k-step, over the first 64 columns of S_t
+#pragma unroll
+              for (int k = 0; k < ROWS / 16; ++k)
+                tc::umma_bf16_ts(tmem + 256u + (uint32_t)(t * 64), tmem + (uint32_t)(t * 128 + k * 8), vd + (uint64_t)(k * ((16 * 128) >> 4)), IDESC_O,
+                                 (uint32_t)((j | k) != 0));
+            } else {
+              const uint64_t pd = tc::smem_desc_k_sw128(p_base + (uint32_t)(t * 2 * TILE_BYTES));
+#pragma unroll
+              for (int k = 0; k < ROWS / 16; ++k)
+                tc::umma_bf16(tmem + 256u + (uint32_t)(t * 64), pd + (uint64_t)((k >> 2) * (TILE_BYTES >> 4)) + 2ull * (k & 3),
+                              vd + (uint64_t)(k * ((16 * 128) >> 4)), IDESC_O, (uint32_t)((j | k) != 0));
+            }
+            tc::umma_commit(&bars->pv_done[t]);
+            if (!SHARED_KV || t == 1) tc::umma_commit(&bars->kv_empty[cs[t]]);      // every MMA that reads this stage has been issued
+            if (more) {                                                             // next block's S tile for the group that just finished
+              if (t == 0 || !SHARED_KV) tc::mbar_wait(&bars->kv_full[ns[t]], nph[t]);
+              tc::tc_fence_after();
+              issue_s(t, qb, ns[t]);
+            }
           }
-          cs = ns;
-          cph = nph;
+          cs[0] = ns[0];
+          cs[1] = ns[1];
+          cph[0] = nph[0];
+          cph[1] = nph[1];
         }
         tc::umma_commit(&bars->q_empty[qb]);
       }
@@ -508,7 +519,7 @@ static int launch_attn_pipe_impl(const CUtensorMap& tq, const CUtensorMap& tkv, 
   KDB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   cudaLaunchConfig_t lc{};
   lc.gridDim = dim3((unsigned)(p.n_pairs < sms ? p.n_pairs : sms));
-  lc.blockDim = dim3(352);
+  lc.blockDim = dim3(320);
   lc.dynamicSmemBytes = PA_SMEM;
   lc.stream = st;
   cudaLaunchAttribute attr[1];
