@@ -193,8 +193,14 @@ def cpu_port_time(O, model, wl, batch, budget_s, t_fwd):
     dt = time.perf_counter() - t0
     nfe = nfe_of(wl["sampler"], steps)
     ips = batch / (dt * full_nfe / nfe)
+    how = "the full schedule, nothing extrapolated" if nfe == full_nfe else "images/s EXTRAPOLATED by the NFE ratio"
     return ips, (f"{batch} image(s) x {nfe} of {full_nfe} model evaluations ({SAMPLER_NAME[wl['sampler']]} {steps} of {wl['steps']} Karras steps) "
-                 f"in {dt:.1f} s, images/s EXTRAPOLATED by the NFE ratio")
+                 f"in {dt:.1f} s, {how}")
+
+
+def cpu_sample_batch(wl, budget_s, t_fwd):
+    """Images in the cpu_baseline sample: as many full schedules as fit the budget (1..8), so a fast host still does ~10 s of work."""
+    return max(1, min(8, int(budget_s / max(t_fwd * nfe_of(wl["sampler"], wl["steps"]), 1e-3))))
 
 
 def run_reference(args, rank, world):
@@ -503,7 +509,7 @@ def main():
             parity = {"error": repr(exc)}
         if world == 1:
             O, cpu_model, cores, t_fwd = cpu_port_setup(wl)
-            v, sample = cpu_port_time(O, cpu_model, wl, 2 if RES <= 256 else 1, args.cpu_seconds, t_fwd)
+            v, sample = cpu_port_time(O, cpu_model, wl, cpu_sample_batch(wl, args.cpu_seconds, t_fwd), args.cpu_seconds, t_fwd)
             cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
 
     if rank == 0:
