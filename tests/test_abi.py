@@ -40,3 +40,27 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     import pytest
     with pytest.raises(_native.NativeLibraryError):
         _native.lib()
+
+
+def test_every_entry_point_rejects_null_arguments_without_touching_the_gpu():
+    """Each compute entry validates its arguments before its first CUDA call: all-NULL / all-zero arguments come back as a
+    negative kdb error code with a message (never a crash, never a cudaError from a launch attempt)."""
+    from k_diffusion import _native
+    L = _native.lib()
+    no_args_or_void = {"kdb_abi_version", "kdb_last_error", "kdb_launch_count", "kdb_launch_breakdown", "kdb_model_destroy",
+                       "kdb_profile_end", "kdb_profile_gate"}          # gate(0 ns) is a legal request: it launches
+    size_queries = {"kdb_model_workspace_bytes": 0, "kdb_model_tap_count": 0}   # return a size, 0 for a NULL model
+    checked = 0
+    for name, (res, args) in _native.SIGNATURES.items():
+        if name in no_args_or_void:
+            continue
+        zeros = [0.0 if a in (ctypes.c_float, ctypes.c_double) else
+                 0 if a in (ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64, ctypes.c_size_t) else None for a in args]
+        rc = getattr(L, name)(*zeros)
+        if name in size_queries:
+            assert rc == size_queries[name], (name, rc)
+        else:
+            assert rc < 0, f"{name}(NULL...) returned {rc}"
+            assert L.kdb_last_error(), name
+        checked += 1
+    assert checked >= 24
