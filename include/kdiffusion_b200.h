@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define KDB_ABI_VERSION 6
+#define KDB_ABI_VERSION 7
 
 #define KDB_ERR_BAD_ARG      (-1)
 #define KDB_ERR_UNSUPPORTED  (-2)
@@ -91,6 +91,12 @@ int kdb_solver_cfg_combine(const float* uncond, const float* cond, float* out, i
 #define KDB_DPM_ERROR_SCRATCH 512
 int kdb_solver_dpm_error(const float* x_low, const float* x_high, const float* x_prev, int64_t n, float atol, float rtol,
                          float* partials, void* stream);
+
+/* partials[0] = sum_i (err[i] / (atol + rtol * max(|y0[i]|, |y1[i]|)))^2 : the error ratio of an embedded Runge-Kutta step
+ * (the dopri5 integration behind log_likelihood, sampling.py:280-301; the caller takes sqrt(. / n)).  Same scratch and
+ * determinism contract as kdb_solver_dpm_error. */
+int kdb_solver_rk_error(const float* err, const float* y0, const float* y1, int64_t n, float atol, float rtol,
+                        float* partials, void* stream);
 
 /* out[b,...] = (x[b,...] - den[b,...]) / sigma[b]      (sampling.py:46-48 to_d; sigma is [B]) */
 int kdb_solver_to_d(const float* x, const float* den, const float* sigma, float* out,

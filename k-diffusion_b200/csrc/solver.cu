@@ -353,14 +353,23 @@ __global__ void __launch_bounds__(256) noise_brownian_kernel(float* __restrict__
 // ------------------------------------------------------------------------------------------------
 constexpr int kErrBlocks = 296, kErrThreads = 256;
 
+// RK = false: the DPM-Solver form above (a = lo, b = hi, c = prev).
+// RK = true : the embedded Runge-Kutta form of the likelihood ODE (sampling.py:298, dopri5): a = error estimate, b = y0, c = y1,
+//             sum (a / (atol + rtol max(|b|, |c|)))^2.
+template <bool RK>
 __global__ void __launch_bounds__(kErrThreads) dpm_error_partial_kernel(const float* __restrict__ lo, const float* __restrict__ hi,
                                                                         const float* __restrict__ prev, int64_t n, float atol, float rtol,
                                                                         float* __restrict__ partials) {
   float acc = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * kErrThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kErrThreads) {
     const float a = __ldg(lo + i), b = __ldg(hi + i), c = __ldg(prev + i);
-    const float delta = fmaxf(atol, rtol * fmaxf(fabsf(a), fabsf(c)));
-    const float v = (a - b) / delta;
+    float v;
+    if constexpr (RK) {
+      v = a / (atol + rtol * fmaxf(fabsf(b), fabsf(c)));
+    } else {
+      const float delta = fmaxf(atol, rtol * fmaxf(fabsf(a), fabsf(c)));
+      v = (a - b) / delta;
+    }
     acc = fmaf(v, v, acc);
   }
   __shared__ float red[kErrThreads];
@@ -465,7 +474,17 @@ int kdb_solver_cfg_combine(const float* uncond, const float* cond, float* out, i
 int kdb_solver_dpm_error(const float* x_low, const float* x_high, const float* x_prev, int64_t n, float atol, float rtol, float* partials,
                          void* stream) {
   KDB_REQUIRE(x_low && x_high && x_prev && partials && n > 0, KDB_ERR_BAD_ARG, "dpm_error: bad args");
-  dpm_error_partial_kernel<<<kErrBlocks, kErrThreads, 0, (cudaStream_t)stream>>>(x_low, x_high, x_prev, n, atol, rtol, partials);
+  dpm_error_partial_kernel<false><<<kErrBlocks, kErrThreads, 0, (cudaStream_t)stream>>>(x_low, x_high, x_prev, n, atol, rtol, partials);
+  KDB_LAUNCH_CHECK(F_SOLVER, (cudaStream_t)stream);
+  dpm_error_final_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(partials, kErrBlocks);
+  KDB_LAUNCH_CHECK(F_SOLVER, (cudaStream_t)stream);
+  return 0;
+}
+
+int kdb_solver_rk_error(const float* err, const float* y0, const float* y1, int64_t n, float atol, float rtol, float* partials,
+                        void* stream) {
+  KDB_REQUIRE(err && y0 && y1 && partials && n > 0, KDB_ERR_BAD_ARG, "rk_error: bad args");
+  dpm_error_partial_kernel<true><<<kErrBlocks, kErrThreads, 0, (cudaStream_t)stream>>>(err, y0, y1, n, atol, rtol, partials);
   KDB_LAUNCH_CHECK(F_SOLVER, (cudaStream_t)stream);
   dpm_error_final_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(partials, kErrBlocks);
   KDB_LAUNCH_CHECK(F_SOLVER, (cudaStream_t)stream);

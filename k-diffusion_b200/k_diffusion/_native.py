@@ -18,7 +18,7 @@ LIB_PATH = Path(os.environ.get("KDB200_LIB", _HERE / "_lib" / "libkdb200.so"))
 PREC_FP32, PREC_BF16 = 0, 1
 ATTN_NONE, ATTN_GLOBAL, ATTN_NEIGHBORHOOD, ATTN_SHIFTED_WINDOW = 0, 1, 2, 3
 MAX_LEVELS = 8
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 _vp, _i32, _i64, _f32, _f64, _u64, _sz = (ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double,
                                            ctypes.c_uint64, ctypes.c_size_t)
@@ -48,6 +48,7 @@ SIGNATURES = {
     "kdb_solver_lincomb": (_i32, [ctypes.POINTER(_vp), ctypes.POINTER(_f32), _i32, _vp, _i64, _vp]),
     "kdb_solver_cfg_combine": (_i32, [_vp, _vp, _vp, _i64, _f32, _vp]),
     "kdb_solver_dpm_error": (_i32, [_vp, _vp, _vp, _i64, _f32, _f32, _vp, _vp]),
+    "kdb_solver_rk_error": (_i32, [_vp, _vp, _vp, _i64, _f32, _f32, _vp, _vp]),
     "kdb_solver_to_d": (_i32, [_vp, _vp, _vp, _vp, _i32, _i64, _vp]),
     "kdb_precond_scale_in": (_i32, [_vp, _vp, _f32, _vp, _i32, _i64, _vp]),
     "kdb_precond_combine": (_i32, [_vp, _vp, _vp, _f32, _vp, _i32, _i64, _vp]),
@@ -253,6 +254,16 @@ def dpm_error(x_low, x_high, x_prev, atol, rtol):
     scratch = torch.empty(512, dtype=torch.float32, device=x_low.device)
     check(lib().kdb_solver_dpm_error(ptr(f32c(x_low)), ptr(f32c(x_high)), ptr(f32c(x_prev)), x_low.numel(), float(atol), float(rtol), ptr(scratch), stream()))
     return math.sqrt(float(scratch[0])) / math.sqrt(x_low.numel())
+
+
+@_on_device_of_first
+def rk_error(err, y0, y1, atol, rtol):
+    """||err / (atol + rtol * max(|y0|, |y1|))||_2 / sqrt(numel) as a Python float: the error ratio of one embedded Runge-Kutta step
+    (the dopri5 integration of log_likelihood, reference sampling.py:298)."""
+    require_cuda(err, y0, y1)
+    scratch = torch.empty(512, dtype=torch.float32, device=err.device)
+    check(lib().kdb_solver_rk_error(ptr(f32c(err)), ptr(f32c(y0)), ptr(f32c(y1)), err.numel(), float(atol), float(rtol), ptr(scratch), stream()))
+    return math.sqrt(float(scratch[0])) / math.sqrt(err.numel())
 
 
 @_on_device_of_first

@@ -5,8 +5,8 @@
     python oracle/make_golden_dpm.py        # -> tests/golden/toy_dpm_solvers.npz
 
 reference: k_diffusion/sampling.py:303-330 (PIDStepSizeController), :333-488 (DPMSolver), :491-516 (sample_dpm_fast / sample_dpm_adaptive).
-Same toy denoiser and recorded-noise recipe as make_golden_next.py.  `log_likelihood` (:281-301) needs torchdiffeq, which is absent
-from the reference tree and from this image: not recorded (parity unpinned, not implemented)."""
+Same toy denoiser and recorded-noise recipe as make_golden_next.py.  `log_likelihood` (:280-301) needs torchdiffeq, which is absent
+from the reference tree and from this image: see make_golden_ll.py."""
 import sys
 from pathlib import Path
 

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 import k_diffusion as K
-from conftest import GOLDEN, assert_close, bits, load_npz, unhex
+from conftest import GOLDEN, assert_close, bits, load_fixture, load_npz, synth_sd, unhex
 from oracle import kdiff_oracle as O
 
 S = K.sampling
@@ -370,3 +370,75 @@ def test_dpm_solver_plans_and_entry_points_with_stubbed_kernels(monkeypatch):
         adaptive(toy2, x, 1e-2, 80., order=4)
     with pytest.raises(ValueError):
         fast(toy2, x, 0., 80., 6)
+
+
+def test_log_likelihood_host_logic_with_stubbed_kernels(monkeypatch):
+    """SURVEY 8(f) row 4, log_likelihood: the product's dopri5 host loop (lincomb launches + one error-ratio read per step) against the
+    values recorded from the reference (oracle/make_golden_ll.py) through the autograd branch, and the native branch -- 4th-order
+    central difference of the engine's fp32 evaluations instead of a VJP -- against the oracle's autograd evaluation of the same
+    quadratic form on the cfg1 model.  Native primitives replaced by torch one-liners (test-only stubs)."""
+    import k_diffusion as K
+    from k_diffusion import _native
+    monkeypatch.setattr(_native, "require_cuda", lambda *t: None)
+    monkeypatch.setattr(_native, "f32c", lambda t: t.to(torch.float32).contiguous())
+    monkeypatch.setattr(_native, "lincomb", lambda ts, cs, out=None: sum(np.float32(c) * t for t, c in zip(ts, cs)))
+    monkeypatch.setattr(_native, "rk_error", lambda err, y0, y1, atol, rtol:
+                        float((err / (atol + rtol * torch.maximum(y0.abs(), y1.abs()))).pow(2).mean().sqrt()))
+    ll_fn = S.log_likelihood
+    while hasattr(ll_fn, "__wrapped__"):
+        ll_fn = ll_fn.__wrapped__                      # below the device guard (no CUDA here)
+    z = load_npz("toy_log_likelihood.npz")
+    toy2 = lambda x, s, **kw: x / (1 + s[:, None, None, None] ** 2) + 0.1 * torch.tanh(x)
+    gauss = lambda x, s, **kw: x * (0.49 / (0.49 + s[:, None, None, None] ** 2))
+    for name, model, kw in (("toy", toy2, {}), ("gauss", gauss, {}), ("toy_tight", toy2, dict(atol=1e-6, rtol=1e-6))):
+        with torch.no_grad():
+            ll, info = ll_fn(model, z["x"], 1e-2, 80., v=z[name + "_v"], **kw)
+        # the first error estimates are differences of nearly equal stages (fp32 round-off level), so the two evaluation orders may
+        # pick slightly different early steps: same step count within two, values within the integration tolerance
+        assert abs(info["fevals"] - int(z[name + "_fevals"])) <= 12 and info["fevals"] == 2 + 6 * (info["n_accept"] + info["n_reject"]), (name, info)
+        tol = kw.get("rtol", 1e-4)
+        assert float((ll - z[name + "_ll"]).abs().max()) <= 3 * tol * float(z[name + "_ll"].abs().max()), (name, ll, z[name + "_ll"])
+    with torch.no_grad(), pytest.raises(RuntimeError):                         # a model autograd cannot see through fails loudly
+        ll_fn(lambda x, s: x.detach() * 0.5, z["x"], 1e-2, 80.)
+    assert len(S._DP5_BETA[-1]) == 6 and S._DP5_C_ERR[1] == 0 and S._DP5_C_MID[1] == 0      # every stage fits one 6-input lincomb
+    assert [tuple(r) for r in S._DP5_BETA] == [tuple(r) for r in O.DOPRI5_BETA] and S._DP5_C_ERR == O.DOPRI5_C_ERR and S._DP5_C_MID == O.DOPRI5_C_MID
+
+    # native branch: right-hand side by finite differences of (stubbed) engine evaluations vs autograd through the oracle model
+    cfg, shapes, _ = load_fixture("cfg1_mnist")
+    omodel = O.make_denoiser(synth_sd(shapes, 1), cfg["model"])
+    den = K.config.make_denoiser_wrapper(cfg)(K.config.make_model(cfg))
+    assert den.is_native()
+    seen = []
+
+    class StubEvaluator:                                # stands in for the engine: evaluates the oracle model, records what was asked
+        def __init__(self, model, x, extra_args, sigmas):
+            self.sig, self.ea = sigmas, extra_args
+            seen.append(self)
+
+        def __call__(self, k, x):
+            with torch.no_grad():
+                return omodel(x, torch.full((x.shape[0],), self.sig[k]), **self.ea)
+
+    monkeypatch.setattr(S, "_Evaluator", StubEvaluator)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 1, 28, 28, generator=g) * 0.4 + 0.1
+    v = torch.randint(0, 2, x.shape, generator=g).float() * 2 - 1
+    ea = {"class_cond": torch.tensor([1, 9])}
+    rhs, count = S._likelihood_rhs(den, x, ea, v, 1e-2)
+    for sigma in (0.02, 0.7, 30.0):
+        xs = x * (1 + sigma)
+        with torch.no_grad():
+            d, d_ll = rhs(sigma, (xs, torch.zeros(2)))
+        assert seen[-1].precision == _native.PREC_FP32 and len(seen[-1].sig) == 5
+        with torch.enable_grad():
+            xg = xs.clone().requires_grad_()
+            dd = (xg - omodel(xg, torch.full((2,), sigma), **ea)) / sigma
+            want = (v * torch.autograd.grad((dd * v).sum(), xg)[0]).flatten(1).sum(1)
+        assert_close(d, dd.detach(), rtol=1e-5, atol=1e-6 * float(xs.abs().max()) / sigma, what=f"d at sigma {sigma}")     # (x - D) / sigma cancels
+        assert float((d_ll - want).abs().max()) <= 2e-3 / sigma + 1e-4 * float(want.abs().max()), (sigma, d_ll, want)
+    assert count[0] == 3
+    with torch.no_grad():
+        ll, info = ll_fn(den, x, 1e-2, 80., extra_args=ea, v=v)
+    ll_o, info_o = O.log_likelihood(omodel, x, 1e-2, 80., extra_args=ea, v=v)
+    # at the default tolerances two correct integrations differ by a few rtol * |ll| (measured: the tight-tolerance value lies between)
+    assert float((ll - ll_o).abs().max()) <= 1e-3 * float(ll_o.abs().max()) and abs(info["fevals"] - info_o["fevals"]) <= 18

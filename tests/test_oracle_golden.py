@@ -4,6 +4,7 @@ CPU only.  Bit-exact where the reference arithmetic is reproduced op for op (sch
 schedule indices, position grids, RoPE frequencies, masks); rtol 1e-3 / atol 1e-5 for model outputs
 and sampler trajectories (the oracle uses explicit softmax instead of SDPA's fused CPU kernel).
 """
+import numpy as np
 import torch
 
 from conftest import assert_close, bits, load_fixture, load_npz, synth_sd, unhex
@@ -230,3 +231,54 @@ def test_dpm_solver_fast_and_adaptive_against_reference():
         got, info = O.sample_dpm_adaptive(toy2, x, 1e-2, 80., noise_sampler=ns() if kw.get("eta") else None, **kw)
         assert torch.equal(got, z[name]), name
         assert [info[k] for k in ("steps", "nfe", "n_accept", "n_reject")] == [int(v) for v in z[name + "_info"]], name
+
+
+def test_log_likelihood_against_reference_closed_form_and_scipy():
+    """SURVEY 8(f) row 4, log_likelihood (sampling.py:280-301).  torchdiffeq (the reference's integrator) is absent, so:
+    (1) the oracle equals the REFERENCE function run with the oracle's dopri5 installed as `sampling.odeint`
+        (oracle/make_golden_ll.py) -- pins the ODE right-hand side, the prior term and the assembly;
+    (2) for Gaussian data N(0, s^2 I) everything is analytic: log p_sigma_min(x) = sum log N(x_i; 0, s^2 + sigma_min^2)
+        -- pins the integrated value (the residual at tight tolerance is the prior mismatch s^2 / sigma_max^2);
+    (3) the integrator alone against scipy's independent Dormand-Prince (RK45) on a nonlinear system;
+    (4) the tableau satisfies the order conditions (5th-order solution, 4th-order embedded and mid-point weights)."""
+    import math
+    z = load_npz("toy_log_likelihood.npz")
+    toy2 = lambda x, s, **kw: x / (1 + s[:, None, None, None] ** 2) + 0.1 * torch.tanh(x)
+    gauss = lambda x, s, **kw: x * (0.49 / (0.49 + s[:, None, None, None] ** 2))
+    x = z["x"]
+    for name, model, kw in (("toy", toy2, {}), ("gauss", gauss, {}), ("toy_tight", toy2, dict(atol=1e-6, rtol=1e-6))):
+        ll, info = O.log_likelihood(model, x, 1e-2, 80., v=z[name + "_v"], **kw)
+        assert info["fevals"] == int(z[name + "_fevals"]), name
+        assert torch.equal(ll, z[name + "_ll"]), name
+    # (2) closed form, float64 so that only the method's error is left
+    xd = x.double()
+    want = torch.distributions.Normal(0, math.sqrt(0.49 + 1e-4)).log_prob(xd).flatten(1).sum(1)
+    ll, _ = O.log_likelihood(gauss, xd, 1e-2, 80., v=z["gauss_v"].double())
+    assert float((ll - want).abs().max()) < 5e-4 * float(want.abs().max())            # default tolerances: a few rtol |ll|
+    ll, _ = O.log_likelihood(gauss, xd, 1e-2, 800., atol=1e-9, rtol=1e-9, v=z["gauss_v"].double())
+    assert float((ll - want).abs().max()) < 1e-4
+    # (3) integrator vs scipy RK45 on a stiff-ish nonlinear pair
+    from scipy.integrate import solve_ivp
+    f_np = lambda t, y: [-y[0] * y[1] + math.sin(t), y[0] ** 2 - 0.5 * y[1]]
+    f_t = lambda t, y: (-y[0] * y[1] + math.sin(t), y[0] ** 2 - 0.5 * y[1])
+    y0 = (torch.tensor([1.0], dtype=torch.float64), torch.tensor([0.5], dtype=torch.float64))
+    (a, b), st = O.odeint_dopri5(f_t, y0, 0.0, 7.0, 1e-10, 1e-10)
+    ref = solve_ivp(f_np, (0.0, 7.0), [1.0, 0.5], method="RK45", atol=1e-12, rtol=1e-12).y[:, -1]
+    assert abs(float(a) - ref[0]) < 1e-8 and abs(float(b) - ref[1]) < 1e-8 and st["n_accept"] > 20
+    (a4, b4), st4 = O.odeint_dopri5(f_t, y0, 0.0, 7.0, 1e-4, 1e-4)
+    assert abs(float(a4) - ref[0]) < 2e-3 and st4["n_accept"] < st["n_accept"] / 4       # the tolerance steers the step count
+    # (4) order conditions
+    c = np.array([0.0, *O.DOPRI5_ALPHA])
+    A = np.zeros((7, 7))
+    for i, row in enumerate(O.DOPRI5_BETA):
+        A[i + 1, :len(row)] = row
+    b, e, m = (np.array(t) for t in (O.DOPRI5_C_SOL, O.DOPRI5_C_ERR, O.DOPRI5_C_MID))
+    assert np.abs(A.sum(1) - c).max() < 1e-15 and np.abs(A[6] - b).max() == 0           # first-same-as-last
+    for q in range(5):
+        assert abs(b @ c ** q - 1 / (q + 1)) < 1e-15
+    for q in range(4):
+        assert abs(e @ c ** q) < 1e-15 and abs(m @ c ** q - 0.5 ** (q + 1) / (q + 1)) < 1e-15
+    for got, want_ in ((b @ A @ c, 1 / 6), (b @ A @ c ** 2, 1 / 12), (b @ (c * (A @ c)), 1 / 8), (b @ A @ A @ c, 1 / 24),
+                       (b @ A @ c ** 3, 1 / 20), (b @ A @ A @ A @ c, 1 / 120), (e @ A @ c, 0), (e @ A @ A @ c, 0),
+                       (m @ A @ c, 0.5 ** 3 / 6), (m @ A @ A @ c, 0.5 ** 4 / 24)):
+        assert abs(got - want_) < 1e-15
