@@ -302,6 +302,9 @@ def lms_coefficient(order, t, i, j):
     return float(0.5 * (b - a) * np.dot(weights, basis))
 
 
+linear_multistep_coeff = lms_coefficient        # the reference's name (sampling.py:247)
+
+
 def plan_lms(sig, order=4):
     if not 1 <= order <= 4:
         raise ValueError('order must be between 1 and 4 (one lincomb launch takes x and four derivative buffers)')
@@ -803,9 +806,11 @@ def sample_dpmpp_2m(model, x, sigmas, extra_args=None, callback=None, disable=No
 # against reference trajectories (tests/test_host_logic.py).  GPU parity tests for these entry points land with round 2.
 # --------------------------------------------------------------------------------------------
 
-def _sample_ops(name, model, x, sigmas, plan_fn, extra_args, callback, disable, params, noise_sampler=None, churn_noise=0., callback_extra=None):
+def _sample_ops(name, model, x, sigmas, plan_fn, extra_args, callback, disable, params, noise_sampler=None, churn_noise=0., callback_extra=None,
+                on_eval=None):
     """Run a generic op plan.  `plan_fn(sig)` builds it from the host copy of `sigmas` (or is the plan itself, a list);
-    `callback_extra(st)` may add keys to the callback payload of a step."""
+    `callback_extra(st)` may add keys to the callback payload of a step; `on_eval()` runs after every model evaluation (like `callback`
+    it keeps the loop out of a CUDA graph)."""
     xw, sig, extra_args = _prepare(x, sigmas, extra_args)
     plan = plan_fn if isinstance(plan_fn, list) else plan_fn(sig)
     needs_noise = any(op[0] == 'noise' for st in plan for op in st['ops'])
@@ -825,6 +830,8 @@ def _sample_ops(name, model, x, sigmas, plan_fn, extra_args, callback, disable, 
                 if kind == 'eval':
                     T[op[1]] = ev(k, T[op[2]])
                     k += 1
+                    if on_eval is not None:
+                        on_eval()
                     if first and callback is not None:
                         callback({'x': T[op[2]], 'i': st['i'], 'sigma': sigmas[st['i']], 'sigma_hat': _scalar_like(sigmas, st['sigma_hat']),
                                   'denoised': T[op[1]], **({} if callback_extra is None else callback_extra(st))})
@@ -839,7 +846,8 @@ def _sample_ops(name, model, x, sigmas, plan_fn, extra_args, callback, disable, 
         return T['x']
 
     # a graph replays the same noise kernels every call: only legal without noise or with the Brownian tree
-    out = _run(name, body, ev, xw, sig, params, callback, noise_sampler=_GLOBAL_RNG if churned else (noise_sampler if needs_noise else None))
+    out = _run(name, body, ev, xw, sig, params, callback if callback is not None else on_eval,
+               noise_sampler=_GLOBAL_RNG if churned else (noise_sampler if needs_noise else None))
     return _finish(out, x)
 
 
@@ -1003,12 +1011,15 @@ def _dpm_ancestral_target(t, t_next, t_end, eta):
     return float(t_down), float(su)
 
 
-def plan_dpm_fast(sigma_min, sigma_max, n, eta=0., s_noise=1.):
-    """Host plan of dpm_solver_fast (sampling.py:403-433): (plan, ts) with ts the fp32 time grid as Python floats."""
+def plan_dpm_fast(sigma_min, sigma_max, n, eta=0., s_noise=1., t_range=None):
+    """Host plan of dpm_solver_fast (sampling.py:403-433): (plan, ts) with ts the fp32 time grid as Python floats.  `t_range` =
+    (t_start, t_end) gives the end points directly (DPMSolver.dpm_solver_fast is called with times, not sigmas)."""
     if sigma_min <= 0 or sigma_max <= 0:
         raise ValueError('sigma_min and sigma_max must not be 0')
     m = math.floor(n / 3) + 1
-    ts = [float(v) for v in torch.linspace(-torch.tensor(float(sigma_max)).log(), -torch.tensor(float(sigma_min)).log(), m + 1)]
+    t_lo, t_hi = (-torch.tensor(float(sigma_max)).log(), -torch.tensor(float(sigma_min)).log()) if t_range is None else \
+                 (torch.tensor(float(t_range[0])), torch.tensor(float(t_range[1])))
+    ts = [float(v) for v in torch.linspace(t_lo, t_hi, m + 1)]
     orders = [3] * (m - 2) + [2, 1] if n % 3 == 0 else [3] * (m - 1) + [n % 3]
     plan = []
     for i, order in enumerate(orders):
@@ -1024,22 +1035,24 @@ def plan_dpm_fast(sigma_min, sigma_max, n, eta=0., s_noise=1.):
 
 @_on_x_device
 @torch.no_grad()
-def sample_dpm_fast(model, x, sigma_min, sigma_max, n, extra_args=None, callback=None, disable=None, eta=0., s_noise=1., noise_sampler=None):
+def sample_dpm_fast(model, x, sigma_min, sigma_max, n, extra_args=None, callback=None, disable=None, eta=0., s_noise=1., noise_sampler=None,
+                    _t_range=None, _on_eval=None):
     """DPM-Solver-Fast (fixed step size). See https://arxiv.org/abs/2206.00927.  (reference sampling.py:491-501)
     With eta = 0 no noise is drawn at all (the reference draws and multiplies by 0: same samples, different global RNG offset)."""
-    plan, ts = plan_dpm_fast(sigma_min, sigma_max, n, eta, s_noise)
+    plan, ts = plan_dpm_fast(sigma_min, sigma_max, n, eta, s_noise, _t_range)
     sigmas = torch.tensor([_dpm_sigma(t) for t in ts], dtype=torch.float32, device=x.device)
     if eta and noise_sampler is None:
         noise_sampler = default_noise_sampler(_native.f32c(x))
     extra = lambda st: {'t': _scalar_like(sigmas, st['t']), 't_up': _scalar_like(sigmas, st['t'])}
     return _sample_ops('dpm_fast', model, x, sigmas, plan, extra_args, callback, disable, (float(sigma_min), float(sigma_max), n, eta, s_noise),
-                       noise_sampler if eta else None, callback_extra=extra)
+                       noise_sampler if eta else None, callback_extra=extra, on_eval=_on_eval)
 
 
 @_on_x_device
 @torch.no_grad()
 def sample_dpm_adaptive(model, x, sigma_min, sigma_max, extra_args=None, callback=None, disable=None, order=3, rtol=0.05, atol=0.0078, h_init=0.05,
-                        pcoeff=0., icoeff=1., dcoeff=0., accept_safety=0.81, eta=0., s_noise=1., noise_sampler=None, return_info=False):
+                        pcoeff=0., icoeff=1., dcoeff=0., accept_safety=0.81, eta=0., s_noise=1., noise_sampler=None, return_info=False,
+                        _t_range=None, _on_eval=None):
     """DPM-Solver-12 and 23 (adaptive step size). See https://arxiv.org/abs/2206.00927.  (reference sampling.py:435-488, :504-516)
     The step size depends on the data: every step reads one error norm back to the host (`kdb_solver_dpm_error`), so this sampler is
     not captured into a CUDA graph.  Model evaluations, state updates and the error reduction are libkdb200 kernels."""
@@ -1053,7 +1066,8 @@ def sample_dpm_adaptive(model, x, sigma_min, sigma_max, extra_args=None, callbac
     ours = isinstance(noise_sampler, (BrownianTreeNoiseSampler, PhiloxNoiseSampler))
     if eta and noise_sampler is None:
         noise_sampler, ours = default_noise_sampler(xc), True
-    t_start, t_end = f32(_dpm_t(sigma_max)), f32(_dpm_t(sigma_min))
+    t_start, t_end = (f32(_dpm_t(sigma_max)), f32(_dpm_t(sigma_min))) if _t_range is None else (f32(_t_range[0]), f32(_t_range[1]))
+    on_eval = (lambda: None) if _on_eval is None else _on_eval
     pid = PIDStepSizeController(abs(h_init), pcoeff, icoeff, dcoeff, 1.5 if eta else order, accept_safety)
     s, x_prev = t_start, xc
     info = {'steps': 0, 'nfe': 0, 'n_accept': 0, 'n_reject': 0}
@@ -1070,12 +1084,14 @@ def sample_dpm_adaptive(model, x, sigma_min, sigma_max, extra_args=None, callbac
             ops = hi_ops[:3] + [lo_ops[3]] + hi_ops[3:]      # u1, den1, eps1 | lo | u2, den2, eps2, hi
         ev = _Evaluator(model, xc, extra_args, [_dpm_sigma(float(s))] + evals)
         T = {'x': xc, 'den': ev(0, xc)}
+        on_eval()
         ops = [_dpm_eps_op('eps', 'x', 'den', _dpm_sigma(float(s)))] + ops
         k = 1
         for op in ops:
             if op[0] == 'eval':
                 T[op[1]] = ev(k, T[op[2]])
                 k += 1
+                on_eval()
             else:
                 T[op[1]] = _native.lincomb([T[n_] for n_, _ in op[2]], [float(c) for _, c in op[2]])
         error = _native.dpm_error(T['lo'], T['hi'], x_prev, atol, rtol)
@@ -1098,6 +1114,47 @@ def sample_dpm_adaptive(model, x, sigma_min, sigma_max, extra_args=None, callbac
                       'denoised': T['den'], 'error': error, 'h': pid.h, **info})
     out = _finish(xc, x)
     return (out, info) if return_info else out
+
+
+class DPMSolver:
+    """DPM-Solver. See https://arxiv.org/abs/2206.00927.  The reference's driver object (sampling.py:333-488) with its constructor and
+    its two entry points; times are t = -log(sigma).  The step formulas themselves are the op plans above (`_dpm_step_ops`), so the
+    reference's `dpm_solver_{1,2,3}_step` / `eps` cache methods have no counterpart here.  Forward (denoising) direction only."""
+
+    def __init__(self, model, extra_args=None, eps_callback=None, info_callback=None):
+        self.model = model
+        self.extra_args = {} if extra_args is None else extra_args
+        self.eps_callback = eps_callback          # called after every model evaluation
+        self.info_callback = info_callback        # called once per step with {'x', 'i', 't', 't_up', 'denoised', ...}
+
+    def t(self, sigma):
+        return -sigma.log()
+
+    def sigma(self, t):
+        return t.neg().exp()
+
+    @staticmethod
+    def _range(t_start, t_end, eta):
+        t_start, t_end = float(t_start), float(t_end)
+        if not t_end > t_start:
+            if eta:
+                raise ValueError('eta must be 0 for reverse sampling')
+            raise NotImplementedError('reverse-time integration (t_end < t_start) is outside the sampling path of this package')
+        return t_start, t_end
+
+    def dpm_solver_fast(self, x, t_start, t_end, nfe, eta=0., s_noise=1., noise_sampler=None):
+        t_start, t_end = self._range(t_start, t_end, eta)
+        return sample_dpm_fast(self.model, x, math.exp(-t_end), math.exp(-t_start), nfe, extra_args=self.extra_args, callback=self.info_callback,
+                               disable=True, eta=eta, s_noise=s_noise, noise_sampler=noise_sampler, _t_range=(t_start, t_end),
+                               _on_eval=self.eps_callback)
+
+    def dpm_solver_adaptive(self, x, t_start, t_end, order=3, rtol=0.05, atol=0.0078, h_init=0.05, pcoeff=0., icoeff=1., dcoeff=0.,
+                            accept_safety=0.81, eta=0., s_noise=1., noise_sampler=None):
+        t_start, t_end = self._range(t_start, t_end, eta)
+        return sample_dpm_adaptive(self.model, x, math.exp(-t_end), math.exp(-t_start), extra_args=self.extra_args, callback=self.info_callback,
+                                   disable=True, order=order, rtol=rtol, atol=atol, h_init=h_init, pcoeff=pcoeff, icoeff=icoeff, dcoeff=dcoeff,
+                                   accept_safety=accept_safety, eta=eta, s_noise=s_noise, noise_sampler=noise_sampler, return_info=True,
+                                   _t_range=(t_start, t_end), _on_eval=self.eps_callback)
 
 
 # --------------------------------------------------------------------------------------------

@@ -370,6 +370,22 @@ def test_dpm_solver_plans_and_entry_points_with_stubbed_kernels(monkeypatch):
         adaptive(toy2, x, 1e-2, 80., order=4)
     with pytest.raises(ValueError):
         fast(toy2, x, 0., 80., 6)
+    # the reference's driver object (sampling.py:333-488): same numbers through DPMSolver, callbacks at the reference's cadence
+    evals, infos = [], []
+    solver = S.DPMSolver(toy2, eps_callback=lambda: evals.append(1), info_callback=infos.append)
+    t_start, t_end = solver.t(torch.tensor(80.)), solver.t(torch.tensor(1e-2))
+    assert float(solver.sigma(t_start)) == pytest.approx(80.)
+    assert_close(solver.dpm_solver_fast(x, t_start, t_end, 10), z["dpm_fast_n10"], rtol=1e-4, atol=2e-5, what="DPMSolver.dpm_solver_fast")
+    assert len(evals) == 10 and [c["i"] for c in infos] == [0, 1, 2, 3] and {"x", "t", "t_up", "denoised"} <= set(infos[0])
+    evals.clear()
+    got, info = solver.dpm_solver_adaptive(x, t_start, t_end)
+    assert [info[k] for k in ("steps", "nfe", "n_accept", "n_reject")] == [int(v) for v in z["dpm_adaptive_o3_info"]] and len(evals) == info["nfe"]
+    assert float((got - z["dpm_adaptive_o3"]).abs().max()) <= 1e-3 * float(z["dpm_adaptive_o3"].abs().max())
+    with pytest.raises(NotImplementedError):
+        solver.dpm_solver_fast(x, t_end, t_start, 10)
+    with pytest.raises(ValueError):
+        solver.dpm_solver_adaptive(x, t_end, t_start, eta=0.5)
+    assert S.linear_multistep_coeff is S.lms_coefficient
 
 
 def test_log_likelihood_host_logic_with_stubbed_kernels(monkeypatch):
