@@ -151,9 +151,9 @@ class BatchedBrownianTree:
             ta, tb = tb, ta
         return _native.noise_brownian(self.like, self.seeds, self.t0, self.t1, ta, tb, self.depth).view(self.shape)
 
-    def __call__(self, ta, tb):
-        w = self.normalized(ta, tb)
-        return _native.lincomb([w], [math.sqrt(abs(float(tb) - float(ta)))])
+    def __call__(self, t0, t1):
+        w = self.normalized(t0, t1)
+        return _native.lincomb([w], [math.sqrt(abs(float(t1) - float(t0)))])
 
 
 class BrownianTreeNoiseSampler:

@@ -458,3 +458,44 @@ def test_log_likelihood_host_logic_with_stubbed_kernels(monkeypatch):
     ll_o, info_o = O.log_likelihood(omodel, x, 1e-2, 80., extra_args=ea, v=v)
     # at the default tolerances two correct integrations differ by a few rtol * |ll| (measured: the tight-tolerance value lies between)
     assert float((ll - ll_o).abs().max()) <= 1e-3 * float(ll_o.abs().max()) and abs(info["fevals"] - info_o["fevals"]) <= 18
+
+
+def test_public_api_matches_reference_signatures():
+    """every public name of the reference's API for the path exists here and is callable with the reference's arguments --
+    same parameter names, order, kinds and defaults (tests/golden/api_signatures.json, recorded by oracle/make_golden_api.py from the real
+    reference).  Extra parameters are allowed only AFTER the reference's, keyword-only or with a default."""
+    import inspect
+    from k_diffusion.models import image_transformer_v2 as itv2
+    ref = json.loads((GOLDEN / "api_signatures.json").read_text())
+    roots = {"sampling": S, "layers": K.layers, "external": K.external, "config": K.config, "utils": K.utils, "models": itv2}
+
+    def same_default(ours, theirs):
+        if ours == theirs:
+            return True
+        if theirs.startswith("<function"):                       # e.g. transform=lambda x: x
+            return ours.startswith("<function")
+        try:
+            return float(eval(ours)) == float(eval(theirs))      # 1.0 / 1. / 1, inf
+        except Exception:
+            return False
+
+    assert len(ref) >= 45
+    for label, want in ref.items():
+        obj = roots[label.split(".")[0]]
+        for part in label.split(".")[1:]:
+            assert hasattr(obj, part), f"{label}: missing"
+            obj = getattr(obj, part)
+        got = [[n, p.kind.name, None if p.default is inspect._empty else repr(p.default)] for n, p in inspect.signature(obj).parameters.items()]
+        if any(w[1] == "VAR_KEYWORD" for w in want):             # **kwargs stays last; named extras may sit in front of it
+            assert any(g[1] == "VAR_KEYWORD" for g in got), f"{label}: **kwargs dropped"
+            want, got = [w for w in want if w[1] != "VAR_KEYWORD"], [g for g in got if g[1] != "VAR_KEYWORD"]
+        head, extra = got[:len(want)], got[len(want):]
+        for g, w in zip(head, want):
+            assert g[0] == w[0] and g[1] == w[1], f"{label}: parameter {g} vs reference {w}"
+            if w[2] is None:
+                assert g[2] is None, f"{label}: {g[0]} gained a default"
+            else:
+                assert g[2] is not None and same_default(g[2], w[2]), f"{label}: default of {g[0]} is {g[2]}, reference {w[2]}"
+        assert len(head) == len(want), f"{label}: parameters missing: {want[len(head):]}"
+        for g in extra:
+            assert g[1] in ("KEYWORD_ONLY", "VAR_KEYWORD") or g[2] is not None, f"{label}: extra required parameter {g}"
