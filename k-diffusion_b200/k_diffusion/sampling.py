@@ -289,11 +289,11 @@ def plan_dpm_2_ancestral(sig, eta=1., s_noise=1.):
 
 def lms_coefficient(order, t, i, j):
     """Integral over [t_i, t_{i+1}] of the j-th Lagrange basis polynomial through t_i, t_{i-1}, ... (sampling.py:247-257).
-    Degree <= order - 1, so 4-node Gauss-Legendre is exact (the reference uses scipy quad with epsrel 1e-4)."""
+    Degree order - 1, so Gauss-Legendre with >= order / 2 nodes is exact (the reference uses scipy quad with epsrel 1e-4)."""
     if order - 1 > i:
         raise ValueError(f'Order {order} too high for step {i}')
     a, b = t[i], t[i + 1]
-    nodes, weights = np.polynomial.legendre.leggauss(4)
+    nodes, weights = np.polynomial.legendre.leggauss(max(4, (order + 1) // 2))
     tau = 0.5 * (b - a) * nodes + 0.5 * (b + a)
     basis = np.ones_like(tau)
     for k in range(order):
@@ -306,12 +306,12 @@ linear_multistep_coeff = lms_coefficient        # the reference's name (sampling
 
 
 def plan_lms(sig, order=4):
-    if not 1 <= order <= 4:
-        raise ValueError('order must be between 1 and 4 (one lincomb launch takes x and four derivative buffers)')
+    if order < 1:
+        raise ValueError('order must be at least 1')
     steps = []
     for i in range(len(sig) - 1):
         cur = min(i + 1, order)
-        # derivative ring d0 (newest) .. d3: rotate names instead of moving data
+        # derivative ring d0 .. d{order-1}: rotate names instead of moving data (x + more than five derivatives: chained launches)
         names = [f'd{(i - j) % order}' for j in range(cur)]
         ops = [('eval', 'den', 'x'), ('lin', names[0], [('x', 1 / sig[i]), ('den', -1 / sig[i])]),
                ('lin', 'x', [('x', 1.)] + [(names[j], lms_coefficient(cur, sig, i, j)) for j in range(cur)])]
@@ -837,7 +837,7 @@ def _sample_ops(name, model, x, sigmas, plan_fn, extra_args, callback, disable, 
                                   'denoised': T[op[1]], **({} if callback_extra is None else callback_extra(st))})
                     first = False
                 elif kind == 'lin':
-                    T[op[1]] = _native.lincomb([T[n] for n, _ in op[2]], [float(c) for _, c in op[2]])
+                    T[op[1]] = _lin_x([(T[n], c) for n, c in op[2]], keep_zero=True)
                 elif kind == 'noise':    # our samplers take host floats (no sync); foreign callables get tensors like the reference
                     args = (op[2], op[3]) if ours else (_scalar_like(sigmas, op[2]), _scalar_like(sigmas, op[3]))
                     T[op[1]] = _native.f32c(noise_sampler(*args))
@@ -1177,9 +1177,9 @@ _DP5_C_MID = (6025192743 / 30085553152 / 2, 0., 51252292925 / 65400821598 / 2, -
               187940372067 / 1594534317056 / 2, -1776094331 / 19743644256 / 2, 11237099 / 235043384 / 2)
 
 
-def _lin_x(terms):
+def _lin_x(terms, keep_zero=False):
     """sum_i c_i t_i over image-sized tensors: libkdb200 lincomb launches of at most six inputs each"""
-    terms = [(t, float(c)) for t, c in terms if c != 0.]
+    terms = [(t, float(c)) for t, c in terms if keep_zero or c != 0.]
     acc = _native.lincomb([t for t, _ in terms[:6]], [c for _, c in terms[:6]])
     for i in range(6, len(terms), 5):
         part = terms[i:i + 5]

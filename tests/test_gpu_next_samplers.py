@@ -49,6 +49,14 @@ def test_opaque_model_next_samplers_vs_reference_trajectories(key):
     assert_close(getattr(S, fn)(toy2, x, sig, disable=True, **kw), z[key], rtol=1e-4, atol=2e-5, what=key)
 
 
+@pytest.mark.parametrize("order", [5, 6, 7, 10])
+def test_sample_lms_any_order_vs_reference(order):
+    """x + more than five derivative buffers: the update is a chain of lincomb launches (oracle/make_golden_lms.py recorded the reference)"""
+    z = load_npz("toy_lms_high_order.npz")
+    got = S.sample_lms(toy2, z["x"].to(DEV), z["sigmas"].to(DEV), disable=True, order=order)
+    assert_close(got, z[f"sample_lms_order{order}"], rtol=1e-4, atol=2e-5, what=f"lms order {order}")
+
+
 def test_native_model_next_samplers_vs_oracle():
     """cfg1 (MNIST transformer, class-conditional, fp32 exact path): CUDA path against the CPU oracle on the same inputs,
     rtol 1e-3 / atol 1e-5, all seven entry points."""

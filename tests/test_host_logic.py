@@ -167,6 +167,12 @@ def test_generic_sampler_entry_points_with_stubbed_kernels(monkeypatch):
     }
     for key, run in runs.items():
         assert_close(run(), z[key], rtol=1e-4, atol=2e-5, what=key)
+    zh = load_npz("toy_lms_high_order.npz")          # any order: x + more than five derivative buffers = chained lincomb launches
+    for o in (5, 6, 7, 10):
+        assert_close(S.sample_lms(toy2, zh["x"], zh["sigmas"], disable=True, order=o), zh[f"sample_lms_order{o}"], rtol=1e-5, atol=5e-6, what=f"lms {o}")
+    assert max(len(op[2]) for st in S.plan_lms(S.host_sigmas(zh["sigmas"]), 10) for op in st["ops"] if op[0] == "lin") == 11
+    with pytest.raises(ValueError):
+        S.sample_lms(toy2, x, sig, disable=True, order=0)
     seen = []
     S.sample_dpmpp_2m_sde(toy2, x, sig, disable=True, noise_sampler=ns(), callback=seen.append)
     assert [c["i"] for c in seen] == list(range(10)) and set(seen[0]) == {"x", "i", "sigma", "sigma_hat", "denoised"}

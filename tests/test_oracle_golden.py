@@ -282,3 +282,12 @@ def test_log_likelihood_against_reference_closed_form_and_scipy():
                        (b @ A @ c ** 3, 1 / 20), (b @ A @ A @ A @ c, 1 / 120), (e @ A @ c, 0), (e @ A @ A @ c, 0),
                        (m @ A @ c, 0.5 ** 3 / 6), (m @ A @ A @ c, 0.5 ** 4 / 24)):
         assert abs(got - want_) < 1e-15
+
+
+def test_sample_lms_any_order_against_reference():
+    """sample_lms accepts any order (sampling.py:260-277); orders 5, 6, 7 and 10 recorded from the reference (oracle/make_golden_lms.py).
+    The oracle's Gauss-Legendre coefficients replace scipy quad (epsrel 1e-4) and land within 1e-6 of its outputs."""
+    z = load_npz("toy_lms_high_order.npz")
+    toy2 = lambda x, s, **kw: x / (1 + s[:, None, None, None] ** 2) + 0.1 * torch.tanh(x)
+    for o in (5, 6, 7, 10):
+        assert_close(O.sample_lms(toy2, z["x"], z["sigmas"], order=o), z[f"sample_lms_order{o}"], rtol=1e-5, atol=2e-6, what=f"lms order {o}")
