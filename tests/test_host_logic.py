@@ -137,7 +137,8 @@ def test_generic_op_plans_reproduce_reference_trajectories():
     with pytest.raises(ValueError):
         S.plan_dpmpp_2m_sde(sig, solver_type="euler")
     with pytest.raises(ValueError):
-        S.plan_lms(sig, order=5)
+        S.plan_lms(sig, order=0)
+    assert max(len(op[2]) for st in S.plan_lms(sig, order=5) for op in st["ops"] if op[0] == "lin") == 6     # x + five derivative buffers
 
 
 def test_generic_sampler_entry_points_with_stubbed_kernels(monkeypatch):
