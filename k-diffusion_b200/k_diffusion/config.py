@@ -92,8 +92,16 @@ def make_model(config):
 
 
 def make_denoiser_wrapper(config):
+    """reference config.py:216-232; the three wrappers differ in their training loss only, `forward` (what sampling calls) is shared"""
     m = config['model']
-    if m.get('has_variance', False) or m.get('loss_config', 'karras') != 'karras':
-        raise ValueError('only the plain Karras denoiser wrapper is in scope')
-    return partial(layers.Denoiser, sigma_data=m.get('sigma_data', 1.), weighting=m.get('loss_weighting', 'karras'),
-                   scales=m.get('loss_scales', 1))
+    sigma_data, has_variance, loss_config = m.get('sigma_data', 1.), m.get('has_variance', False), m.get('loss_config', 'karras')
+    if loss_config == 'karras':
+        weighting = m.get('loss_weighting', 'karras')
+        if not has_variance:
+            return partial(layers.Denoiser, sigma_data=sigma_data, weighting=weighting, scales=m.get('loss_scales', 1))
+        return partial(layers.DenoiserWithVariance, sigma_data=sigma_data, weighting=weighting)
+    if loss_config == 'simple':
+        if has_variance:
+            raise ValueError('Simple loss config does not support a variance output')
+        return partial(layers.SimpleLossDenoiser, sigma_data=sigma_data)
+    raise ValueError('Unknown loss config type')

@@ -52,6 +52,14 @@ class Denoiser(nn.Module):
         return _native.precond_combine(_native.f32c(f), x, sig, float(self.sigma_data))
 
 
+class DenoiserWithVariance(Denoiser):
+    """reference layers.py:93-101: differs from Denoiser in `loss` only (training, out of scope); sampling is identical."""
+
+
+class SimpleLossDenoiser(Denoiser):
+    """L_simple with the Karras et al. preconditioner (reference layers.py:104-113): differs from Denoiser in `loss` only."""
+
+
 class FourierFeatures(nn.Module):
     """Random Fourier features buffer (layers.py:285-293); evaluated inside the engine's conditioning kernel."""
 

@@ -506,3 +506,17 @@ def test_public_api_matches_reference_signatures():
         assert len(head) == len(want), f"{label}: parameters missing: {want[len(head):]}"
         for g in extra:
             assert g[1] in ("KEYWORD_ONLY", "VAR_KEYWORD") or g[2] is not None, f"{label}: extra required parameter {g}"
+
+
+def test_denoiser_wrapper_variants_follow_reference_config():
+    """config.py:216-232: 'karras' (+ has_variance) and 'simple' loss configs select wrappers that differ in the training loss only."""
+    base = json.loads((GOLDEN / "cfg1_mnist_shapes.json").read_text())["config"]
+    mk = lambda **kw: K.config.make_denoiser_wrapper({"model": {**base["model"], **kw}})
+    assert mk().func is K.layers.Denoiser and mk().keywords["sigma_data"] == base["model"]["sigma_data"]
+    assert mk(has_variance=True).func is K.layers.DenoiserWithVariance and "scales" not in mk(has_variance=True).keywords
+    assert mk(loss_config="simple").func is K.layers.SimpleLossDenoiser and set(mk(loss_config="simple").keywords) == {"sigma_data"}
+    assert issubclass(K.layers.SimpleLossDenoiser, K.Denoiser) and K.layers.SimpleLossDenoiser.forward is K.Denoiser.forward
+    with pytest.raises(ValueError):
+        mk(loss_config="simple", has_variance=True)
+    with pytest.raises(ValueError):
+        mk(loss_config="vp")
