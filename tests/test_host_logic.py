@@ -520,3 +520,18 @@ def test_denoiser_wrapper_variants_follow_reference_config():
         mk(loss_config="simple", has_variance=True)
     with pytest.raises(ValueError):
         mk(loss_config="vp")
+
+
+def test_sample_script_command_line_matches_reference():
+    """sample.py (reference sample.py:17-31): same flags and defaults; the additions are optional."""
+    import runpy
+    from conftest import ROOT
+    mod = runpy.run_path(str(ROOT / "k-diffusion_b200" / "sample.py"), run_name="sample_script")
+    a = mod["cli"](["--checkpoint", "m.safetensors"])
+    assert (a.batch_size, a.n, a.steps, a.prefix, a.config) == (64, 64, 50, "out", None) and str(a.checkpoint) == "m.safetensors"
+    assert (a.seed, a.precision, a.sampler) == (None, "fp32", "sample_lms")
+    with pytest.raises(SystemExit):
+        mod["cli"]([])                                                       # --checkpoint is required
+    assert mod["image_shape"]({"input_size": [32, 32], "input_channels": 3}) == (3, 32, 32)
+    with pytest.raises(SystemExit):
+        mod["image_shape"]({"input_size": [32, 64], "input_channels": 3})
