@@ -236,6 +236,23 @@ def test_opaque_model_samplers_vs_golden():
     assert torch.equal(x, x0) and out.dtype == x.dtype and out.device == x.device
 
 
+@pytest.mark.parametrize("name,fn,kw", [("euler_churn20", "sample_euler", dict(s_churn=20.)),
+                                        ("heun_churn3_window", "sample_heun", dict(s_churn=3., s_tmin=0.1, s_tmax=30., s_noise=1.1)),
+                                        ("dpm_2_churn2", "sample_dpm_2", dict(s_churn=2.))])
+def test_churn_vs_reference_with_replayed_draws(name, fn, kw, monkeypatch):
+    """s_churn > 0 against the reference (oracle/make_golden_churn.py).  Noise is only drawn on steps with gamma > 0 (quirk Q1), so the
+    reference's recorded draws of exactly those steps are replayed."""
+    z = load_npz("toy_churn.npz")
+    toy2 = lambda x, s, **k: x / (1 + s[:, None, None, None] ** 2) + 0.1 * torch.tanh(x)
+    n = len(z["sigmas"]) - 1
+    gamma = lambda s_: min(kw["s_churn"] / n, 2 ** 0.5 - 1) if kw.get("s_tmin", 0.) <= float(s_) <= kw.get("s_tmax", float("inf")) else 0.
+    it = iter([z[name + "_eps"][i].to(DEV) for i in range(n) if gamma(z["sigmas"][i]) > 0])
+    monkeypatch.setattr(torch, "randn_like", lambda t, *a, **k: next(it))
+    got = getattr(S, fn)(toy2, z["x"].to(DEV), z["sigmas"].to(DEV), disable=True, **kw)
+    assert_close(got, z[name], rtol=1e-4, atol=2e-5, what=name)
+    assert next(it, None) is None
+
+
 def test_churn_matches_statistics():
     toy = lambda x, s, **kw: 0.5 * x
     x = torch.ones(4, 1, 64, 64, device=DEV)

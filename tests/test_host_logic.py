@@ -535,3 +535,30 @@ def test_sample_script_command_line_matches_reference():
     assert mod["image_shape"]({"input_size": [32, 32], "input_channels": 3}) == (3, 32, 32)
     with pytest.raises(SystemExit):
         mod["image_shape"]({"input_size": [32, 64], "input_channels": 3})
+
+
+def test_karras_churn_entry_points_with_stubbed_kernels(monkeypatch):
+    """s_churn > 0 through the product's plans (sample_euler / sample_heun fused-step kernels, sample_dpm_2 op plan) against the reference
+    outputs of oracle/make_golden_churn.py.  The product draws noise only on steps with gamma > 0 (quirk Q1): it is fed the reference's
+    draws of exactly those steps.  Native primitives replaced by torch one-liners (test-only stubs)."""
+    from k_diffusion import _native
+    f = np.float32
+    monkeypatch.setattr(_native, "require_cuda", lambda *t: None)
+    monkeypatch.setattr(_native, "f32c", lambda t: t.to(torch.float32).contiguous())
+    monkeypatch.setattr(_native, "lincomb", lambda ts, cs, out=None: sum(f(c) * t for t, c in zip(ts, cs)))
+    monkeypatch.setattr(_native, "euler_step", lambda x, den, r, noise=None, cn=0.0, out=None: x + (x - den) * f(r) + (0 if noise is None else noise * f(cn)))
+    monkeypatch.setattr(_native, "heun_correct", lambda x, d1, x2, d2, a1, a2, out=None: x + ((x - d1) * f(a1) + (x2 - d2) * f(a2)))
+    z = load_npz("toy_churn.npz")
+    toy2 = lambda x, s, **kw: x / (1 + s[:, None, None, None] ** 2) + 0.1 * torch.tanh(x)
+    sig = S.host_sigmas(z["sigmas"])
+    cases = {"euler_churn20": (S.sample_euler, S.plan_euler, dict(s_churn=20.)),
+             "heun_churn3_window": (S.sample_heun, S.plan_heun, dict(s_churn=3., s_tmin=0.1, s_tmax=30., s_noise=1.1)),
+             "dpm_2_churn2": (S.sample_dpm_2, S.plan_dpm_2, dict(s_churn=2.))}
+    for name, (fn, plan_fn, kw) in cases.items():
+        plan = plan_fn(sig, **{k: v for k, v in kw.items() if k != "s_noise"})
+        active = [st["i"] for st in plan if st.get("gamma", 0) > 0]
+        assert active and (name != "heun_churn3_window" or len(active) < len(plan))           # the window case skips steps
+        it = iter([z[name + "_eps"][i] for i in active])
+        monkeypatch.setattr(torch, "randn_like", lambda t, *a, **k: next(it))
+        assert_close(fn(toy2, z["x"], z["sigmas"], disable=True, **kw), z[name], rtol=1e-4, atol=2e-5, what=name)
+        assert next(it, None) is None                                                          # every recorded draw of an active step was used

@@ -291,3 +291,20 @@ def test_sample_lms_any_order_against_reference():
     toy2 = lambda x, s, **kw: x / (1 + s[:, None, None, None] ** 2) + 0.1 * torch.tanh(x)
     for o in (5, 6, 7, 10):
         assert_close(O.sample_lms(toy2, z["x"], z["sigmas"], order=o), z[f"sample_lms_order{o}"], rtol=1e-5, atol=2e-6, what=f"lms order {o}")
+
+
+CHURN_CASES = {"euler_churn20": ("sample_euler", dict(s_churn=20.)),
+               "heun_churn3_window": ("sample_heun", dict(s_churn=3., s_tmin=0.1, s_tmax=30., s_noise=1.1)),
+               "dpm_2_churn2": ("sample_dpm_2", dict(s_churn=2.))}
+
+
+def test_karras_churn_against_reference(monkeypatch):
+    """s_churn > 0 (sampling.py:121-127, :162-169, :192-198): gamma, sigma_hat and the injected noise, with the reference's own
+    per-step randn_like draws replayed (oracle/make_golden_churn.py).  The oracle draws on every step like the reference."""
+    z = load_npz("toy_churn.npz")
+    toy2 = lambda x, s, **kw: x / (1 + s[:, None, None, None] ** 2) + 0.1 * torch.tanh(x)
+    for name, (fn, kw) in CHURN_CASES.items():
+        it = iter(z[name + "_eps"])
+        monkeypatch.setattr(torch, "randn_like", lambda t, *a, **k: next(it))
+        got = getattr(O, fn)(toy2, z["x"], z["sigmas"], **kw)
+        assert torch.equal(got, z[name]), (name, float((got - z[name]).abs().max()))
