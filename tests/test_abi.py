@@ -64,3 +64,29 @@ def test_every_entry_point_rejects_null_arguments_without_touching_the_gpu():
             assert L.kdb_last_error(), name
         checked += 1
     assert checked >= 24
+
+
+def test_header_is_plain_c_and_a_c_program_links(tmp_path):
+    """The boundary is a C ABI, not a C++ one: the header compiles as pedantic C99 and a C program that calls into the
+    library links against libkdb200.so and runs without a GPU (kdb_abi_version, kdb_last_error, an argument-validation failure)."""
+    import shutil
+    import subprocess
+    import pytest
+    from k_diffusion import _native
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stdio.h>\n#include <string.h>\n#include "kdiffusion_b200.h"\n'
+                   'int main(void) {\n'
+                   '  if (kdb_abi_version() != KDB_ABI_VERSION) return 1;\n'
+                   '  if (kdb_solver_lincomb(NULL, NULL, 0, NULL, 0, NULL) >= 0) return 2;\n'
+                   '  if (strlen(kdb_last_error()) == 0) return 3;\n'
+                   '  printf("abi %d\\n", kdb_abi_version());\n'
+                   '  return 0;\n}\n')
+    inc, libdir = str(ROOT / "include"), str(_native.LIB_PATH.parent)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-fsyntax-only", str(src)], check=True)
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-l:" + _native.LIB_PATH.name,
+                    "-Wl,-rpath," + libdir, "-Wl,--unresolved-symbols=ignore-in-shared-libs"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    assert out.strip() == f"abi {_native.ABI_VERSION}"
