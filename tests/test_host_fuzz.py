@@ -132,3 +132,40 @@ def test_dpm_solvers_match_oracle_on_random_arguments(monkeypatch):
             if info == winfo:      # (a decision sitting exactly on the accept threshold may flip under a 1e-7 change of the error norm)
                 assert float((got - want).abs().max()) <= 2e-3 * scale, ("dpm_adaptive", kw, eta, smin, smax, float((got - want).abs().max()))
     assert same_decisions >= 27          # of 30 adaptive runs
+
+
+def test_schedules_and_discrete_schedule_bit_identical_on_random_arguments():
+    """Host-side schedule math is the reference's own torch op sequence: bit-identical to the oracle (which the KATs pin to the reference)
+    for random arguments -- the four sigma schedules, get_ancestral_step on fp32 tensors, and DiscreteSchedule's int64 / interpolated
+    sigma_to_t, t_to_sigma and get_sigmas on random tables."""
+    rng = random.Random(2)
+    for _ in range(200):
+        n = rng.randint(1, 60)
+        smin = 10 ** rng.uniform(-3, 0)
+        smax = smin * 10 ** rng.uniform(0.1, 4)
+        rho = rng.uniform(0.5, 9)
+        assert torch.equal(S.get_sigmas_karras(n, smin, smax, rho=rho), O.get_sigmas_karras(n, smin, smax, rho=rho))
+        assert torch.equal(S.get_sigmas_exponential(n, smin, smax), O.get_sigmas_exponential(n, smin, smax))
+        assert torch.equal(S.get_sigmas_polyexponential(n, smin, smax, rho=rho / 4), O.get_sigmas_polyexponential(n, smin, smax, rho=rho / 4))
+        bd, bm, eps = rng.uniform(5, 25), rng.uniform(0.05, 0.5), 10 ** rng.uniform(-4, -2)
+        assert torch.equal(S.get_sigmas_vp(n, beta_d=bd, beta_min=bm, eps_s=eps), O.get_sigmas_vp(n, beta_d=bd, beta_min=bm, eps_s=eps))
+        a, b = torch.tensor(smax, dtype=torch.float32), torch.tensor(smin, dtype=torch.float32)
+        for eta in (0., 0.3, 1., 2.5):
+            got, want = S.get_ancestral_step(a, b, eta), O.get_ancestral_step(a, b, eta)
+            assert all(float(g) == float(w) for g, w in zip(got, want)), (smax, smin, eta, got, want)
+    for _ in range(40):
+        m = rng.randint(2, 1000)
+        lo = 10 ** rng.uniform(-3, -1)
+        table = torch.exp(torch.linspace(math.log(lo), math.log(lo * 10 ** rng.uniform(1, 4)), m)
+                          + 0.3 * torch.rand(m, generator=torch.Generator().manual_seed(m)).cumsum(0) / m)
+        quantize = rng.random() < 0.5
+        ours, ref = K.external.DiscreteSchedule(table, quantize), O.DiscreteScheduleOracle(table, quantize)
+        q = torch.exp(torch.empty(64).uniform_(math.log(lo) - 1, float(table[-1].log()) + 1, generator=torch.Generator().manual_seed(m + 1)))
+        for qz in (None, True, False):
+            got, want = ours.sigma_to_t(q, quantize=qz), ref.sigma_to_t(q, quantize=qz)
+            assert got.dtype == want.dtype and torch.equal(got, want)
+        t = torch.empty(64).uniform_(0, m - 1, generator=torch.Generator().manual_seed(m + 2))
+        assert torch.equal(ours.t_to_sigma(t), ref.t_to_sigma(t))
+        k = rng.randint(1, 50)
+        assert torch.equal(ours.get_sigmas(k), ref.get_sigmas(k)) and torch.equal(ours.get_sigmas(), ref.get_sigmas())
+        assert float(ours.sigma_min) == float(table[0]) and float(ours.sigma_max) == float(table[-1])
