@@ -90,3 +90,10 @@ def test_header_is_plain_c_and_a_c_program_links(tmp_path):
                     "-Wl,-rpath," + libdir, "-Wl,--unresolved-symbols=ignore-in-shared-libs"], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
     assert out.strip() == f"abi {_native.ABI_VERSION}"
+
+
+def test_integration_guide_names_every_entry_point():
+    """INTEGRATION.md is the reference-side binding guide: it must mention every function the header declares."""
+    doc = (ROOT / "INTEGRATION.md").read_text()
+    missing = [n for n in _declared() if n not in doc]
+    assert not missing, missing
